@@ -1,0 +1,264 @@
+"""Host-side Python mirror of the reference's quantification interface, over the C ABI (include/sbq.h).
+
+Everything numeric runs in libsbq.so on the GPU; this module only marshals arrays. If the CUDA
+library is missing or no B200 is visible, the calls raise - there is no CPU path here.
+
+Mirrored reference interfaces (file:line under the ruolin/strawberry checkout):
+  EmSolver.init / run / _theta                 include/estimate.hpp:230-257, src/estimate.cpp:366-488
+  Quantifier.submit* / run / results           LocusContext::estimate_abundances (src/estimate.cpp:279-364)
+                                               + the TPM tail of Sample::procSample (src/alignments.cpp:1821-1829)
+"""
+import ctypes
+import os
+import weakref
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsbq.so")
+
+SBQ_SUCCESS, SBQ_ERR_INVALID, SBQ_ERR_NO_DEVICE, SBQ_ERR_CUDA, SBQ_ERR_NOMEM, SBQ_ERR_STATE, SBQ_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+LOCUS_OK, LOCUS_ITER_CAP, LOCUS_ZERO_DENOM, LOCUS_NO_ROWS = 0, 1, 2, 3
+
+# every symbol include/sbq.h declares (tests check that the library exports all of them)
+ABI_SYMBOLS = [
+    "sbq_abi_version", "sbq_error_string", "sbq_last_error", "sbq_config_default", "sbq_create", "sbq_destroy",
+    "sbq_submit", "sbq_submit_flat", "sbq_clear", "sbq_validate", "sbq_host_alloc", "sbq_host_free",
+    "sbq_upload", "sbq_solve", "sbq_download", "sbq_run", "sbq_fpkm_sum", "sbq_fpkm_sum_to_device",
+    "sbq_finalize_tpm", "sbq_results", "sbq_get_stats", "sbq_em_solve", "sbq_set_plan",
+]
+
+
+class SbqError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"sbq error {code}: {msg}")
+        self.code = code
+
+
+class Config(ctypes.Structure):
+    _fields_ = [("device", ctypes.c_int32), ("max_iter", ctypes.c_int32), ("theta_tol", ctypes.c_double),
+                ("row_eps", ctypes.c_double), ("min_iso_frac", ctypes.c_double),
+                ("effective_len_norm", ctypes.c_int32), ("insert_mean", ctypes.c_double),
+                ("bias_mode", ctypes.c_int32)]
+
+
+class Locus(ctypes.Structure):
+    _fields_ = [("n_iso", ctypes.c_int32), ("n_row", ctypes.c_int32), ("row_ptr", ctypes.c_void_p),
+                ("col", ctypes.c_void_p), ("alpha", ctypes.c_void_p), ("count", ctypes.c_void_p),
+                ("iso_len", ctypes.c_void_p)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int64) for n in ("n_loci", "n_row", "n_iso", "nnz", "loci_warp", "loci_cta", "loci_grid",
+                                              "kernel_launches", "h2d_bytes", "d2h_bytes")] + \
+               [(n, ctypes.c_double) for n in ("upload_ms", "solve_ms", "download_ms", "em_ms", "grid_em_ms")] + \
+               [(n, ctypes.c_int64) for n in ("em_iters_total", "frag_iters", "alg_bytes", "grid_alg_bytes")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib():
+    """Load libsbq.so. Fails loudly when it has not been built (python -m strawberry_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build the CUDA extension first "
+                               "(python -m strawberry_b200.build or __graft_entry__.build()); there is no CPU fallback")
+        L = ctypes.CDLL(LIB_PATH)
+        L.sbq_error_string.restype = ctypes.c_char_p
+        L.sbq_last_error.restype = ctypes.c_char_p
+        L.sbq_last_error.argtypes = [ctypes.c_void_p]
+        L.sbq_host_alloc.restype = ctypes.c_void_p
+        L.sbq_host_alloc.argtypes = [ctypes.c_size_t]
+        L.sbq_host_free.argtypes = [ctypes.c_void_p]
+        L.sbq_config_default.argtypes = [ctypes.POINTER(Config)]
+        L.sbq_create.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(ctypes.c_void_p)]
+        L.sbq_destroy.argtypes = [ctypes.c_void_p]
+        for name in ("sbq_clear", "sbq_validate", "sbq_upload", "sbq_download"):
+            getattr(L, name).argtypes = [ctypes.c_void_p]
+        L.sbq_submit.argtypes = [ctypes.c_void_p, ctypes.POINTER(Locus), ctypes.c_int64]
+        L.sbq_submit_flat.argtypes = [ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 7
+        L.sbq_solve.argtypes = [ctypes.c_void_p, ctypes.c_int64]
+        L.sbq_run.argtypes = [ctypes.c_void_p, ctypes.c_int64]
+        L.sbq_fpkm_sum.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
+        L.sbq_fpkm_sum_to_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.sbq_finalize_tpm.argtypes = [ctypes.c_void_p, ctypes.c_double]
+        L.sbq_results.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 7
+        L.sbq_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(Stats)]
+        L.sbq_em_solve.argtypes = [ctypes.c_void_p, ctypes.POINTER(Locus), ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32)]
+        L.sbq_set_plan.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        _lib = L
+    return _lib
+
+
+def default_config(**overrides):
+    cfg = Config()
+    lib().sbq_config_default(ctypes.byref(cfg))
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise TypeError(f"unknown sbq_config field {k!r}")
+        setattr(cfg, k, v)
+    return cfg
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+def pinned_empty(n, dtype):
+    """numpy array over page-locked memory from sbq_host_alloc (freed when the array is collected)."""
+    dtype = np.dtype(dtype)
+    nbytes = max(int(n) * dtype.itemsize, 1)
+    p = lib().sbq_host_alloc(nbytes)
+    if not p:
+        raise SbqError(SBQ_ERR_NOMEM, "sbq_host_alloc failed (no CUDA device?)")
+    buf = (ctypes.c_char * nbytes).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(n))
+    weakref.finalize(buf, lib().sbq_host_free, p)
+    return arr
+
+
+def pinned_batch(batch):
+    """Copy a flat batch (strawberry_b200.synth layout) into page-locked arrays."""
+    spec = dict(loc_row_off=np.int64, loc_iso_off=np.int64, row_ptr=np.int64, col=np.int32, alpha=np.float64,
+                count=np.int32, iso_len=np.int32)
+    out = dict(batch)
+    for k, dt in spec.items():
+        a = pinned_empty(len(batch[k]), dt)
+        a[...] = batch[k]
+        out[k] = a
+    return out
+
+
+class Quantifier:
+    """One GPU context: queue loci, run the EM + FPKM/frac/TPM epilogue, read results back."""
+
+    def __init__(self, **config):
+        self._L = lib()
+        self.cfg = default_config(**config)
+        h = ctypes.c_void_p()
+        rc = self._L.sbq_create(ctypes.byref(self.cfg), ctypes.byref(h))
+        if rc != SBQ_SUCCESS:
+            raise SbqError(rc, self._L.sbq_error_string(rc).decode())
+        self._h = h
+        self._keepalive = []
+        self._fin = weakref.finalize(self, self._L.sbq_destroy, h)
+
+    def close(self):
+        self._fin()
+
+    def _chk(self, rc):
+        if rc < 0:
+            msg = self._L.sbq_last_error(self._h).decode() or self._L.sbq_error_string(rc).decode()
+            raise SbqError(rc, msg)
+        return rc
+
+    def clear(self):
+        self._keepalive = []
+        self._chk(self._L.sbq_clear(self._h))
+
+    def set_plan(self, force_tier=0, force_cluster=0):
+        self._chk(self._L.sbq_set_plan(self._h, int(force_tier), int(force_cluster)))
+
+    def submit_flat(self, batch):
+        a = [_c(batch["loc_row_off"], np.int64), _c(batch["loc_iso_off"], np.int64), _c(batch["row_ptr"], np.int64),
+             _c(batch["col"], np.int32), _c(batch["alpha"], np.float64), _c(batch["count"], np.int32),
+             _c(batch["iso_len"], np.int32)]
+        self._keepalive.append(a)   # borrowed in place when page-locked
+        self._chk(self._L.sbq_submit_flat(self._h, len(a[0]) - 1, *[_ptr(x) for x in a]))
+
+    def submit(self, loci):
+        """loci: iterable of (n_iso, row_ptr, col, alpha, count, iso_len)."""
+        arr, keep = [], []
+        for n_iso, row_ptr, col, alpha, count, iso_len in loci:
+            rp, c, a = _c(row_ptr, np.int64), _c(col, np.int32), _c(alpha, np.float64)
+            n, il = _c(count, np.int32), _c(iso_len, np.int32)
+            keep.append((rp, c, a, n, il))
+            arr.append(Locus(int(n_iso), len(n), rp.ctypes.data, c.ctypes.data, a.ctypes.data, n.ctypes.data, il.ctypes.data))
+        buf = (Locus * len(arr))(*arr)
+        self._chk(self._L.sbq_submit(self._h, buf, len(arr)))
+
+    def validate(self):
+        self._chk(self._L.sbq_validate(self._h))
+
+    def upload(self):
+        self._chk(self._L.sbq_upload(self._h))
+
+    def solve(self, total_mapped_reads):
+        self._chk(self._L.sbq_solve(self._h, int(total_mapped_reads)))
+
+    def download(self):
+        self._chk(self._L.sbq_download(self._h))
+
+    def run(self, total_mapped_reads):
+        self._chk(self._L.sbq_run(self._h, int(total_mapped_reads)))
+
+    def fpkm_sum(self):
+        s = ctypes.c_double(0)
+        self._chk(self._L.sbq_fpkm_sum(self._h, ctypes.byref(s)))
+        return s.value
+
+    def fpkm_sum_to_device(self, dev_ptr):
+        self._chk(self._L.sbq_fpkm_sum_to_device(self._h, ctypes.c_void_p(dev_ptr)))
+
+    def finalize_tpm(self, global_fpkm_sum):
+        self._chk(self._L.sbq_finalize_tpm(self._h, float(global_fpkm_sum)))
+
+    def stats(self):
+        s = Stats()
+        self._chk(self._L.sbq_get_stats(self._h, ctypes.byref(s)))
+        return s.as_dict()
+
+    def results(self):
+        st = self.stats()
+        ni, nl = st["n_iso"], st["n_loci"]
+        out = dict(theta=np.empty(ni), fpkm=np.empty(ni), frac=np.empty(ni), tpm=np.empty(ni),
+                   keep=np.empty(ni, np.int32), iters=np.empty(nl, np.int32), status=np.empty(nl, np.int32))
+        self._chk(self._L.sbq_results(self._h, *[_ptr(out[k]) for k in ("theta", "fpkm", "frac", "tpm", "keep", "iters", "status")]))
+        return out
+
+    def em_solve(self, n_iso, row_ptr, col, alpha, count):
+        rp, c, a, n = _c(row_ptr, np.int64), _c(col, np.int32), _c(alpha, np.float64), _c(count, np.int32)
+        il = np.full(n_iso, 1000, np.int32)
+        loc = Locus(int(n_iso), len(n), rp.ctypes.data, c.ctypes.data, a.ctypes.data, n.ctypes.data, il.ctypes.data)
+        theta = np.empty(n_iso)
+        iters = ctypes.c_int32(0)
+        st = self._chk(self._L.sbq_em_solve(self._h, ctypes.byref(loc), _ptr(theta), ctypes.byref(iters)))
+        return st, theta, iters.value
+
+
+class EmSolver:
+    """Drop-in for the reference's EmSolver (include/estimate.hpp:230-257).
+
+    init(num_iso, count, model) -> bool and run() -> bool keep the reference's meaning
+    (src/estimate.cpp:366-409, :411-488); `_theta` holds the abundances. The solve itself is
+    sbq_em_solve on the GPU; init() only reshapes the dense model into CSR rows.
+    """
+
+    def __init__(self, quantifier=None):
+        self._q = quantifier or Quantifier()
+        self._theta = []
+        self._status = None
+        self.iters = 0
+
+    def init(self, num_iso, count, model):
+        model = np.asarray(model, dtype=np.float64).reshape(len(count), num_iso)
+        rows, cols = np.nonzero(model)
+        row_ptr = np.zeros(len(count) + 1, np.int64)
+        np.cumsum(np.bincount(rows, minlength=len(count)), out=row_ptr[1:])
+        st, theta, it = self._q.em_solve(num_iso, row_ptr, cols.astype(np.int32), model[rows, cols], count)
+        self._status, self._theta, self.iters = st, list(theta), it
+        return st != LOCUS_NO_ROWS
+
+    def run(self):
+        if self._status is None or self._status == LOCUS_NO_ROWS:
+            return False
+        return self._status != LOCUS_ZERO_DENOM

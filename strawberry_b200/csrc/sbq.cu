@@ -1,0 +1,805 @@
+// sbq.cu - runtime + C ABI (include/sbq.h) of the B200-native quantification engine.
+//
+// Host side of the hot path: stages submitted loci into one flat, pinned CSR batch, plans the
+// kernel tiers (warp / cluster / grid) by locus size, moves the batch to HBM, launches the EM
+// kernels of sbq_kernels.cuh on concurrent streams and brings the per-isoform results back.
+// Replaces, for everything numeric, the loop body of Sample::procSample -> quantifyCluster ->
+// LocusContext::estimate_abundances -> EmSolver (reference src/alignments.cpp:1756-1829,
+// src/estimate.cpp:279-488). There is no CPU fallback in this file by design.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sbq.h"
+#include "sbq_kernels.cuh"
+#include "sbq_grid.cuh"
+
+using namespace sbq;
+
+namespace {
+
+constexpr size_t SMEM_CAP = 200 * 1024;   // dynamic shared memory we ask for at most (227 KB usable)
+constexpr int N_SIDE_STREAMS = 12;
+
+// ---- pinned host array with geometric growth -------------------------------------------------
+template <typename T>
+struct PinnedVec {
+   T* p = nullptr;
+   size_t n = 0, cap = 0;
+   bool reserve(size_t want) {
+      if (want <= cap) return true;
+      size_t ncap = std::max(want, cap + cap / 2 + 1024);
+      T* q = nullptr;
+      if (cudaMallocHost((void**)&q, ncap * sizeof(T)) != cudaSuccess) return false;
+      if (n) memcpy(q, p, n * sizeof(T));
+      if (p) cudaFreeHost(p);
+      p = q;
+      cap = ncap;
+      return true;
+   }
+   bool append(const T* src, size_t k) {
+      if (!reserve(n + k)) return false;
+      if (k) memcpy(p + n, src, k * sizeof(T));
+      n += k;
+      return true;
+   }
+   void clear() { n = 0; }
+   void release() {
+      if (p) cudaFreeHost(p);
+      p = nullptr;
+      n = cap = 0;
+   }
+};
+
+struct DevBuf {
+   void* p = nullptr;
+   size_t cap = 0;
+   bool reserve(size_t bytes) {
+      if (bytes <= cap) return true;
+      if (p) cudaFree(p);
+      p = nullptr;
+      cap = 0;
+      size_t want = bytes + bytes / 8 + 4096;
+      if (cudaMalloc(&p, want) != cudaSuccess) return false;
+      cap = want;
+      return true;
+   }
+   void release() {
+      if (p) cudaFree(p);
+      p = nullptr;
+      cap = 0;
+   }
+};
+
+struct LaunchClass {      // one kernel launch of the cluster tier
+   int cs, lpr;
+   std::vector<int32_t> loci;
+   int max_iso = 0;
+   size_t list_off = 0;   // offset into the device list buffer
+   size_t smem = 0;
+};
+
+}  // namespace
+
+struct sbq_ctx {
+   sbq_config cfg;
+   int device = 0;
+   cudaDeviceProp prop;
+   cudaStream_t stream = nullptr;
+   cudaStream_t side[N_SIDE_STREAMS] = {};
+   cudaEvent_t ev[10] = {};
+   cudaEvent_t ev_fork = nullptr, ev_join[N_SIDE_STREAMS] = {};
+   std::mutex mu;
+   std::string err;
+
+   // staged batch (host, pinned)
+   PinnedVec<int64_t> h_loc_row_off, h_loc_iso_off, h_row_ptr;
+   PinnedVec<int32_t> h_col, h_count, h_iso_len;
+   PinnedVec<double> h_alpha;
+   // borrowed flat batch (caller-pinned arrays used in place)
+   bool borrowed = false;
+   const int64_t *b_loc_row_off = nullptr, *b_loc_iso_off = nullptr, *b_row_ptr = nullptr;
+   const int32_t *b_col = nullptr, *b_count = nullptr, *b_iso_len = nullptr;
+   const double* b_alpha = nullptr;
+   int64_t n_loci = 0, n_row = 0, n_iso = 0, nnz = 0;
+
+   // plan
+   int force_tier = 0, force_cluster = 0;
+   std::vector<int32_t> warp_list, grid_list;
+   std::vector<LaunchClass> classes;
+   int warp_max_iso = 1;
+   PinnedVec<int32_t> h_lists;
+   size_t warp_list_off = 0, grid_list_off = 0;
+
+   // device
+   DevBuf d_in, d_out, d_lists, d_grid_scratch;
+   DevParams dp{};
+   double* d_tpm = nullptr;
+   double* d_fpkm_sum = nullptr;
+   int32_t* d_lists_p = nullptr;
+   bool resident = false, solved = false, downloaded = false;
+
+   // results (host, pinned)
+   PinnedVec<double> r_theta, r_fpkm, r_frac, r_tpm, r_locus_fpkm;
+   PinnedVec<int32_t> r_keep, r_iters, r_status;
+   double r_fpkm_sum = 0.0;
+
+   sbq_stats stats{};
+};
+
+namespace {
+
+int fail(sbq_ctx* c, int code, const char* fmt, ...) {
+   if (c) {
+      char buf[512];
+      va_list ap;
+      va_start(ap, fmt);
+      vsnprintf(buf, sizeof buf, fmt, ap);
+      va_end(ap);
+      c->err = buf;
+   }
+   return code;
+}
+
+#define CU(call)                                                                                   \
+   do {                                                                                            \
+      cudaError_t e_ = (call);                                                                     \
+      if (e_ != cudaSuccess)                                                                       \
+         return fail(c, SBQ_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+   } while (0)
+
+const int64_t* loc_row_off(const sbq_ctx* c) { return c->borrowed ? c->b_loc_row_off : c->h_loc_row_off.p; }
+const int64_t* loc_iso_off(const sbq_ctx* c) { return c->borrowed ? c->b_loc_iso_off : c->h_loc_iso_off.p; }
+const int64_t* row_ptr(const sbq_ctx* c) { return c->borrowed ? c->b_row_ptr : c->h_row_ptr.p; }
+const int32_t* colp(const sbq_ctx* c) { return c->borrowed ? c->b_col : c->h_col.p; }
+const int32_t* countp(const sbq_ctx* c) { return c->borrowed ? c->b_count : c->h_count.p; }
+const int32_t* iso_lenp(const sbq_ctx* c) { return c->borrowed ? c->b_iso_len : c->h_iso_len.p; }
+const double* alphap(const sbq_ctx* c) { return c->borrowed ? c->b_alpha : c->h_alpha.p; }
+
+bool is_pinned(const void* p) {
+   cudaPointerAttributes a;
+   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+   }
+   return a.type == cudaMemoryTypeHost;
+}
+
+// copy a borrowed batch into our own staging (needed before anything else is appended)
+int materialise(sbq_ctx* c) {
+   if (!c->borrowed) return SBQ_SUCCESS;
+   bool ok = true;
+   c->h_loc_row_off.clear(); c->h_loc_iso_off.clear(); c->h_row_ptr.clear();
+   c->h_col.clear(); c->h_count.clear(); c->h_iso_len.clear(); c->h_alpha.clear();
+   ok &= c->h_loc_row_off.append(c->b_loc_row_off, c->n_loci + 1);
+   ok &= c->h_loc_iso_off.append(c->b_loc_iso_off, c->n_loci + 1);
+   ok &= c->h_row_ptr.append(c->b_row_ptr, c->n_row + 1);
+   ok &= c->h_col.append(c->b_col, c->nnz);
+   ok &= c->h_alpha.append(c->b_alpha, c->nnz);
+   ok &= c->h_count.append(c->b_count, c->n_row);
+   ok &= c->h_iso_len.append(c->b_iso_len, c->n_iso);
+   c->borrowed = false;
+   return ok ? SBQ_SUCCESS : fail(c, SBQ_ERR_NOMEM, "pinned staging allocation failed");
+}
+
+void reset_batch(sbq_ctx* c) {
+   c->borrowed = false;
+   c->h_loc_row_off.clear(); c->h_loc_iso_off.clear(); c->h_row_ptr.clear();
+   c->h_col.clear(); c->h_count.clear(); c->h_iso_len.clear(); c->h_alpha.clear();
+   c->n_loci = c->n_row = c->n_iso = c->nnz = 0;
+   c->resident = c->solved = c->downloaded = false;
+}
+
+int ensure_origin(sbq_ctx* c) {
+   if (c->h_loc_row_off.n == 0) {
+      int64_t z = 0;
+      if (!c->h_loc_row_off.append(&z, 1) || !c->h_loc_iso_off.append(&z, 1) || !c->h_row_ptr.append(&z, 1))
+         return fail(c, SBQ_ERR_NOMEM, "pinned staging allocation failed");
+   }
+   return SBQ_SUCCESS;
+}
+
+template <int LPR, int NT>
+size_t cluster_class_smem(int max_iso) {
+   size_t want = ((size_t)5 * max_iso + 8 + (size_t)(NT / LPR) * max_iso) * sizeof(double);
+   return std::min(want, SMEM_CAP);
+}
+
+int cluster_size_for(int64_t nnz) {
+   if (nnz <= 6 * 1024) return 1;
+   if (nnz <= 16 * 1024) return 2;
+   if (nnz <= 40 * 1024) return 4;
+   if (nnz <= 100 * 1024) return 8;
+   return 16;
+}
+
+// ---- planner: tier per locus, launch classes, work lists sorted by descending size -------------
+int plan(sbq_ctx* c) {
+   const int64_t* lro = loc_row_off(c);
+   const int64_t* lio = loc_iso_off(c);
+   const int64_t* rp = row_ptr(c);
+   c->warp_list.clear();
+   c->grid_list.clear();
+   c->classes.clear();
+   c->warp_max_iso = 1;
+   std::vector<int64_t> nnz_of(c->n_loci);
+   LaunchClass* slot[5][2] = {};
+   std::vector<LaunchClass> tmp;
+   tmp.reserve(10);
+   const int64_t grid_min_nnz = 2 * 1000 * 1000;
+   for (int64_t l = 0; l < c->n_loci; ++l) {
+      const int64_t R = lro[l + 1] - lro[l], T = lio[l + 1] - lio[l];
+      const int64_t nnz = rp[lro[l + 1]] - rp[lro[l]];
+      nnz_of[l] = nnz;
+      if (T > SBQ_MAX_ISO) return fail(c, SBQ_ERR_UNSUPPORTED, "locus %lld has %lld isoforms (> SBQ_MAX_ISO)", (long long)l, (long long)T);
+      int tier;
+      if (c->force_tier) tier = c->force_tier;
+      else if (T <= WT_MAX_ISO && nnz <= 2048) tier = 1;
+      else if (nnz >= grid_min_nnz) tier = 3;
+      else tier = 2;
+      if (tier == 1 && T > WT_MAX_ISO) tier = 2;
+      if (tier == 3 && !grid_tier_supports((int)T)) tier = 2;
+      if (tier == 1) {
+         c->warp_list.push_back((int32_t)l);
+         c->warp_max_iso = std::max(c->warp_max_iso, (int)T);
+      } else if (tier == 3) {
+         c->grid_list.push_back((int32_t)l);
+      } else {
+         int cs = c->force_cluster ? c->force_cluster : cluster_size_for(nnz);
+         int csi = cs == 1 ? 0 : cs == 2 ? 1 : cs == 4 ? 2 : cs == 8 ? 3 : 4;
+         int lpr = (R > 0 && nnz / R >= 12) ? 32 : 8;
+         int li = lpr == 32 ? 1 : 0;
+         if (!slot[csi][li]) {
+            tmp.push_back(LaunchClass{cs, lpr, {}, 0, 0, 0});
+            slot[csi][li] = &tmp.back();
+         }
+         slot[csi][li]->loci.push_back((int32_t)l);
+         slot[csi][li]->max_iso = std::max(slot[csi][li]->max_iso, (int)T);
+      }
+   }
+   auto by_size = [&](int32_t a, int32_t b) { return nnz_of[a] != nnz_of[b] ? nnz_of[a] > nnz_of[b] : a < b; };
+   std::sort(c->warp_list.begin(), c->warp_list.end(), by_size);
+   std::sort(c->grid_list.begin(), c->grid_list.end(), by_size);
+   for (auto& lc : tmp) {
+      std::sort(lc.loci.begin(), lc.loci.end(), by_size);
+      lc.smem = lc.lpr == 32 ? cluster_class_smem<32, 512>(lc.max_iso) : cluster_class_smem<8, 256>(lc.max_iso);
+      int G = lc.lpr == 32 ? cluster_groups_for<32, 512>(lc.max_iso, lc.smem) : cluster_groups_for<8, 256>(lc.max_iso, lc.smem);
+      if (G <= 0) return fail(c, SBQ_ERR_UNSUPPORTED, "locus with %d isoforms does not fit the cluster tier", lc.max_iso);
+      c->classes.push_back(std::move(lc));
+   }
+   // biggest clusters first: they sit on the critical path
+   std::sort(c->classes.begin(), c->classes.end(), [](const LaunchClass& a, const LaunchClass& b) { return a.cs > b.cs; });
+
+   c->h_lists.clear();
+   c->warp_list_off = 0;
+   if (!c->h_lists.append(c->warp_list.data(), c->warp_list.size())) return fail(c, SBQ_ERR_NOMEM, "list staging");
+   c->grid_list_off = c->h_lists.n;
+   if (!c->h_lists.append(c->grid_list.data(), c->grid_list.size())) return fail(c, SBQ_ERR_NOMEM, "list staging");
+   for (auto& lc : c->classes) {
+      lc.list_off = c->h_lists.n;
+      if (!c->h_lists.append(lc.loci.data(), lc.loci.size())) return fail(c, SBQ_ERR_NOMEM, "list staging");
+   }
+   c->stats.loci_warp = (int64_t)c->warp_list.size();
+   c->stats.loci_grid = (int64_t)c->grid_list.size();
+   c->stats.loci_cta = c->n_loci - c->stats.loci_warp - c->stats.loci_grid;
+   return SBQ_SUCCESS;
+}
+
+size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+template <typename K>
+int set_kernel_attrs(sbq_ctx* c, K kernel, size_t smem, bool nonportable) {
+   CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+   if (nonportable) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+   return SBQ_SUCCESS;
+}
+
+template <int LPR, int NT>
+int launch_cluster_class(sbq_ctx* c, const LaunchClass& lc, cudaStream_t st) {
+   auto kernel = em_cluster_kernel<LPR, NT>;
+   int rc = set_kernel_attrs(c, kernel, lc.smem, lc.cs > 8);
+   if (rc) return rc;
+   cudaLaunchConfig_t cfg{};
+   cfg.gridDim = dim3((unsigned)(lc.loci.size() * lc.cs));
+   cfg.blockDim = dim3(NT);
+   cfg.dynamicSmemBytes = lc.smem;
+   cfg.stream = st;
+   cudaLaunchAttribute attr[1];
+   attr[0].id = cudaLaunchAttributeClusterDimension;
+   attr[0].val.clusterDim.x = (unsigned)lc.cs;
+   attr[0].val.clusterDim.y = 1;
+   attr[0].val.clusterDim.z = 1;
+   cfg.attrs = attr;
+   cfg.numAttrs = 1;
+   const int32_t* list = c->d_lists_p + lc.list_off;
+   CU(cudaLaunchKernelEx(&cfg, kernel, c->dp, list, (int)lc.loci.size(), (unsigned)lc.smem));
+   return SBQ_SUCCESS;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int sbq_abi_version(void) { return SBQ_ABI_VERSION; }
+
+const char* sbq_error_string(int err) {
+   switch (err) {
+      case SBQ_SUCCESS: return "success";
+      case SBQ_ERR_INVALID: return "invalid argument";
+      case SBQ_ERR_NO_DEVICE: return "no CUDA device (libsbq has no CPU path)";
+      case SBQ_ERR_CUDA: return "CUDA runtime error";
+      case SBQ_ERR_NOMEM: return "out of memory";
+      case SBQ_ERR_STATE: return "invalid call sequence";
+      case SBQ_ERR_UNSUPPORTED: return "shape outside supported limits";
+      default: return "unknown error";
+   }
+}
+
+const char* sbq_last_error(const sbq_ctx* c) { return c ? c->err.c_str() : ""; }
+
+void sbq_config_default(sbq_config* cfg) {
+   if (!cfg) return;
+   memset(cfg, 0, sizeof *cfg);
+   cfg->device = -1;
+   cfg->max_iter = 1000;
+   cfg->theta_tol = 1e-2;
+   cfg->row_eps = 1e-5;
+   cfg->min_iso_frac = 0.0;
+   cfg->effective_len_norm = 0;
+   cfg->insert_mean = 0.0;
+   cfg->bias_mode = 0;
+}
+
+int sbq_create(const sbq_config* cfg, sbq_ctx** out) {
+   if (!cfg || !out) return SBQ_ERR_INVALID;
+   *out = nullptr;
+   if (cfg->max_iter < 1 || !(cfg->theta_tol >= 0) || cfg->bias_mode < 0 || cfg->bias_mode > 1) return SBQ_ERR_INVALID;
+   int ndev = 0;
+   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+      cudaGetLastError();
+      return SBQ_ERR_NO_DEVICE;
+   }
+   int dev = cfg->device;
+   if (dev < 0) {
+      if (cudaGetDevice(&dev) != cudaSuccess) return SBQ_ERR_NO_DEVICE;
+   }
+   if (dev >= ndev) return SBQ_ERR_INVALID;
+   sbq_ctx* c = new sbq_ctx();
+   c->cfg = *cfg;
+   c->device = dev;
+   auto bail = [&](int code) { sbq_destroy(c); return code; };
+   if (cudaSetDevice(dev) != cudaSuccess) return bail(SBQ_ERR_CUDA);
+   if (cudaGetDeviceProperties(&c->prop, dev) != cudaSuccess) return bail(SBQ_ERR_CUDA);
+   if (c->prop.major < 10) return bail(SBQ_ERR_NO_DEVICE);   // sm_100a code only
+   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SBQ_ERR_CUDA);
+   for (auto& s : c->side)
+      if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return bail(SBQ_ERR_CUDA);
+   for (auto& e : c->ev)
+      if (cudaEventCreate(&e) != cudaSuccess) return bail(SBQ_ERR_CUDA);
+   if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail(SBQ_ERR_CUDA);
+   for (auto& e : c->ev_join)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(SBQ_ERR_CUDA);
+   *out = c;
+   return SBQ_SUCCESS;
+}
+
+void sbq_destroy(sbq_ctx* c) {
+   if (!c) return;
+   cudaSetDevice(c->device);
+   if (c->stream) cudaStreamSynchronize(c->stream);
+   c->h_loc_row_off.release(); c->h_loc_iso_off.release(); c->h_row_ptr.release();
+   c->h_col.release(); c->h_count.release(); c->h_iso_len.release(); c->h_alpha.release();
+   c->h_lists.release();
+   c->r_theta.release(); c->r_fpkm.release(); c->r_frac.release(); c->r_tpm.release();
+   c->r_locus_fpkm.release(); c->r_keep.release(); c->r_iters.release(); c->r_status.release();
+   c->d_in.release(); c->d_out.release(); c->d_lists.release(); c->d_grid_scratch.release();
+   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+   for (auto& e : c->ev_join) if (e) cudaEventDestroy(e);
+   for (auto& s : c->side) if (s) cudaStreamDestroy(s);
+   if (c->stream) cudaStreamDestroy(c->stream);
+   delete c;
+}
+
+int sbq_set_plan(sbq_ctx* c, int force_tier, int force_cluster) {
+   if (!c) return SBQ_ERR_INVALID;
+   if (force_tier < 0 || force_tier > 3) return fail(c, SBQ_ERR_INVALID, "force_tier must be 0..3");
+   if (force_cluster != 0 && force_cluster != 1 && force_cluster != 2 && force_cluster != 4 && force_cluster != 8 && force_cluster != 16)
+      return fail(c, SBQ_ERR_INVALID, "force_cluster must be 0, 1, 2, 4, 8 or 16");
+   c->force_tier = force_tier;
+   c->force_cluster = force_cluster;
+   c->resident = false;
+   return SBQ_SUCCESS;
+}
+
+int sbq_clear(sbq_ctx* c) {
+   if (!c) return SBQ_ERR_INVALID;
+   std::lock_guard<std::mutex> lk(c->mu);
+   reset_batch(c);
+   return SBQ_SUCCESS;
+}
+
+int sbq_submit(sbq_ctx* c, const sbq_locus* loci, int64_t n_loci) {
+   if (!c || (!loci && n_loci > 0) || n_loci < 0) return SBQ_ERR_INVALID;
+   std::lock_guard<std::mutex> lk(c->mu);
+   cudaSetDevice(c->device);
+   int rc = materialise(c);
+   if (rc) return rc;
+   if ((rc = ensure_origin(c))) return rc;
+   for (int64_t l = 0; l < n_loci; ++l) {
+      const sbq_locus& L = loci[l];
+      if (L.n_iso < 1 || L.n_row < 0 || !L.row_ptr || !L.iso_len || (L.n_row > 0 && !L.count))
+         return fail(c, SBQ_ERR_INVALID, "locus %lld: bad shape or null pointer", (long long)l);
+      if (L.n_iso > SBQ_MAX_ISO) return fail(c, SBQ_ERR_UNSUPPORTED, "locus %lld: %d isoforms > SBQ_MAX_ISO", (long long)l, L.n_iso);
+      const int64_t k0 = L.row_ptr[0], k1 = L.row_ptr[L.n_row];
+      if (k1 < k0 || (k1 > k0 && (!L.col || !L.alpha))) return fail(c, SBQ_ERR_INVALID, "locus %lld: bad row_ptr", (long long)l);
+      const int64_t base = c->nnz - k0;
+      if (!c->h_row_ptr.reserve(c->h_row_ptr.n + L.n_row)) return fail(c, SBQ_ERR_NOMEM, "pinned staging");
+      for (int32_t i = 1; i <= L.n_row; ++i) {
+         if (L.row_ptr[i] < L.row_ptr[i - 1]) return fail(c, SBQ_ERR_INVALID, "locus %lld: row_ptr not monotone", (long long)l);
+         c->h_row_ptr.p[c->h_row_ptr.n++] = L.row_ptr[i] + base;
+      }
+      bool ok = c->h_col.append(L.col + k0, k1 - k0) && c->h_alpha.append(L.alpha + k0, k1 - k0) &&
+                c->h_count.append(L.count, L.n_row) && c->h_iso_len.append(L.iso_len, L.n_iso);
+      c->nnz += k1 - k0;
+      c->n_row += L.n_row;
+      c->n_iso += L.n_iso;
+      c->n_loci += 1;
+      ok = ok && c->h_loc_row_off.append(&c->n_row, 1) && c->h_loc_iso_off.append(&c->n_iso, 1);
+      if (!ok) return fail(c, SBQ_ERR_NOMEM, "pinned staging");
+   }
+   c->resident = c->solved = c->downloaded = false;
+   return SBQ_SUCCESS;
+}
+
+int sbq_submit_flat(sbq_ctx* c, int64_t n_loci, const int64_t* lro, const int64_t* lio, const int64_t* rp,
+                    const int32_t* col, const double* alpha, const int32_t* count, const int32_t* iso_len) {
+   if (!c || n_loci < 0) return SBQ_ERR_INVALID;
+   if (n_loci == 0) return SBQ_SUCCESS;
+   if (!lro || !lio || !rp || !iso_len) return fail(c, SBQ_ERR_INVALID, "null offset array");
+   std::lock_guard<std::mutex> lk(c->mu);
+   cudaSetDevice(c->device);
+   const int64_t rows = lro[n_loci] - lro[0], isos = lio[n_loci] - lio[0];
+   if (rows < 0 || isos < n_loci) return fail(c, SBQ_ERR_INVALID, "bad locus offsets");
+   const int64_t k0 = rp[lro[0]], k1 = rp[lro[n_loci]];
+   if (k1 < k0 || (k1 > k0 && (!col || !alpha)) || (rows > 0 && !count)) return fail(c, SBQ_ERR_INVALID, "bad CSR arrays");
+   for (int64_t l = 0; l < n_loci; ++l) {
+      const int64_t T = lio[l + 1] - lio[l];
+      if (lro[l + 1] < lro[l] || T < 1) return fail(c, SBQ_ERR_INVALID, "locus %lld: bad shape", (long long)l);
+      if (T > SBQ_MAX_ISO) return fail(c, SBQ_ERR_UNSUPPORTED, "locus %lld: %lld isoforms > SBQ_MAX_ISO", (long long)l, (long long)T);
+   }
+   // zero-copy: a first, origin-based submission whose arrays are already page-locked is used in place
+   if (c->n_loci == 0 && lro[0] == 0 && lio[0] == 0 && k0 == 0 && is_pinned(lro) && is_pinned(lio) && is_pinned(rp) &&
+       is_pinned(iso_len) && (rows == 0 || is_pinned(count)) && (k1 == 0 || (is_pinned(col) && is_pinned(alpha)))) {
+      c->borrowed = true;
+      c->b_loc_row_off = lro; c->b_loc_iso_off = lio; c->b_row_ptr = rp;
+      c->b_col = col; c->b_alpha = alpha; c->b_count = count; c->b_iso_len = iso_len;
+      c->n_loci = n_loci; c->n_row = rows; c->n_iso = isos; c->nnz = k1;
+      c->resident = c->solved = c->downloaded = false;
+      return SBQ_SUCCESS;
+   }
+   int rc = materialise(c);
+   if (rc) return rc;
+   if ((rc = ensure_origin(c))) return rc;
+   bool ok = c->h_loc_row_off.reserve(c->h_loc_row_off.n + n_loci) && c->h_loc_iso_off.reserve(c->h_loc_iso_off.n + n_loci) &&
+             c->h_row_ptr.reserve(c->h_row_ptr.n + rows);
+   if (!ok) return fail(c, SBQ_ERR_NOMEM, "pinned staging");
+   for (int64_t l = 1; l <= n_loci; ++l) {
+      c->h_loc_row_off.p[c->h_loc_row_off.n++] = c->n_row + (lro[l] - lro[0]);
+      c->h_loc_iso_off.p[c->h_loc_iso_off.n++] = c->n_iso + (lio[l] - lio[0]);
+   }
+   const int64_t base = c->nnz - k0;
+   for (int64_t i = 1; i <= rows; ++i) c->h_row_ptr.p[c->h_row_ptr.n++] = rp[lro[0] + i] + base;
+   ok = c->h_col.append(col + k0, k1 - k0) && c->h_alpha.append(alpha + k0, k1 - k0) &&
+        c->h_count.append(count + lro[0], rows) && c->h_iso_len.append(iso_len + lio[0], isos);
+   if (!ok) return fail(c, SBQ_ERR_NOMEM, "pinned staging");
+   c->n_loci += n_loci; c->n_row += rows; c->n_iso += isos; c->nnz += k1 - k0;
+   c->resident = c->solved = c->downloaded = false;
+   return SBQ_SUCCESS;
+}
+
+int sbq_validate(sbq_ctx* c) {
+   if (!c) return SBQ_ERR_INVALID;
+   std::lock_guard<std::mutex> lk(c->mu);
+   const int64_t *lro = loc_row_off(c), *lio = loc_iso_off(c), *rp = row_ptr(c);
+   const int32_t* col = colp(c);
+   for (int64_t l = 0; l < c->n_loci; ++l) {
+      const int64_t T = lio[l + 1] - lio[l];
+      for (int64_t i = lro[l]; i < lro[l + 1]; ++i) {
+         if (rp[i + 1] < rp[i]) return fail(c, SBQ_ERR_INVALID, "locus %lld row %lld: row_ptr not monotone", (long long)l, (long long)(i - lro[l]));
+         for (int64_t k = rp[i]; k < rp[i + 1]; ++k) {
+            if (col[k] < 0 || col[k] >= T) return fail(c, SBQ_ERR_INVALID, "locus %lld: column %d out of range", (long long)l, col[k]);
+            if (k > rp[i] && col[k] <= col[k - 1]) return fail(c, SBQ_ERR_INVALID, "locus %lld row %lld: columns not strictly ascending", (long long)l, (long long)(i - lro[l]));
+         }
+      }
+   }
+   return SBQ_SUCCESS;
+}
+
+int sbq_upload(sbq_ctx* c) {
+   if (!c) return SBQ_ERR_INVALID;
+   std::lock_guard<std::mutex> lk(c->mu);
+   CU(cudaSetDevice(c->device));
+   if (c->n_loci == 0) return fail(c, SBQ_ERR_STATE, "nothing submitted");
+   int rc = plan(c);
+   if (rc) return rc;
+
+   const size_t sz_lro = align_up((c->n_loci + 1) * sizeof(int64_t)), sz_rp = align_up((c->n_row + 1) * sizeof(int64_t));
+   const size_t sz_col = align_up(c->nnz * sizeof(int32_t)), sz_al = align_up(c->nnz * sizeof(double));
+   const size_t sz_cnt = align_up(c->n_row * sizeof(int32_t)), sz_il = align_up(c->n_iso * sizeof(int32_t));
+   const size_t in_bytes = 2 * sz_lro + sz_rp + sz_col + sz_al + 2 * sz_cnt + sz_il;
+   const size_t sz_iso_d = align_up(c->n_iso * sizeof(double)), sz_iso_i = align_up(c->n_iso * sizeof(int32_t));
+   const size_t sz_loc_i = align_up(c->n_loci * sizeof(int32_t)), sz_loc_d = align_up(c->n_loci * sizeof(double));
+   const size_t out_bytes = 4 * sz_iso_d + sz_iso_i + 2 * sz_loc_i + sz_loc_d + 256;
+   if (!c->d_in.reserve(in_bytes) || !c->d_out.reserve(out_bytes) || !c->d_lists.reserve(align_up(c->h_lists.n * sizeof(int32_t)) + 256))
+      return fail(c, SBQ_ERR_NOMEM, "device allocation failed (%zu MB)", (in_bytes + out_bytes) >> 20);
+
+   char* p = (char*)c->d_in.p;
+   DevParams& dp = c->dp;
+   auto carve = [&](size_t bytes) { char* q = p; p += bytes; return q; };
+   int64_t* d_lro = (int64_t*)carve(sz_lro);
+   int64_t* d_lio = (int64_t*)carve(sz_lro);
+   int64_t* d_rp = (int64_t*)carve(sz_rp);
+   int32_t* d_col = (int32_t*)carve(sz_col);
+   double* d_al = (double*)carve(sz_al);
+   int32_t* d_cnt = (int32_t*)carve(sz_cnt);
+   dp.neff = (int32_t*)carve(sz_cnt);
+   int32_t* d_il = (int32_t*)carve(sz_il);
+   dp.loc_row_off = d_lro; dp.loc_iso_off = d_lio; dp.row_ptr = d_rp; dp.col = d_col; dp.alpha = d_al;
+   dp.count = d_cnt; dp.iso_len = d_il;
+   p = (char*)c->d_out.p;
+   dp.theta = (double*)carve(sz_iso_d);
+   dp.fpkm = (double*)carve(sz_iso_d);
+   dp.frac = (double*)carve(sz_iso_d);
+   c->d_tpm = (double*)carve(sz_iso_d);
+   dp.keep = (int32_t*)carve(sz_iso_i);
+   dp.iters = (int32_t*)carve(sz_loc_i);
+   dp.status = (int32_t*)carve(sz_loc_i);
+   dp.locus_fpkm = (double*)carve(sz_loc_d);
+   c->d_fpkm_sum = (double*)carve(256);
+   c->d_lists_p = (int32_t*)c->d_lists.p;
+
+   cudaStream_t st = c->stream;
+   CU(cudaEventRecord(c->ev[0], st));
+   CU(cudaMemcpyAsync(d_lro, loc_row_off(c), (c->n_loci + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(d_lio, loc_iso_off(c), (c->n_loci + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(d_rp, row_ptr(c), (c->n_row + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+   if (c->nnz) {
+      CU(cudaMemcpyAsync(d_col, colp(c), c->nnz * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(d_al, alphap(c), c->nnz * sizeof(double), cudaMemcpyHostToDevice, st));
+   }
+   if (c->n_row) CU(cudaMemcpyAsync(d_cnt, countp(c), c->n_row * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(d_il, iso_lenp(c), c->n_iso * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+   if (c->h_lists.n) CU(cudaMemcpyAsync(c->d_lists_p, c->h_lists.p, c->h_lists.n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+   CU(cudaEventRecord(c->ev[1], st));
+   CU(cudaStreamSynchronize(st));   // borrowed host arrays may be released after this returns
+   float ms = 0;
+   CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+   c->stats.upload_ms = ms;
+   c->stats.h2d_bytes = 2 * (c->n_loci + 1) * 8 + (c->n_row + 1) * 8 + c->nnz * 12 + c->n_row * 4 + c->n_iso * 4 + (int64_t)c->h_lists.n * 4;
+   c->stats.n_loci = c->n_loci; c->stats.n_row = c->n_row; c->stats.n_iso = c->n_iso; c->stats.nnz = c->nnz;
+   c->resident = true;
+   c->solved = c->downloaded = false;
+   return SBQ_SUCCESS;
+}
+
+int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
+   if (!c) return SBQ_ERR_INVALID;
+   std::lock_guard<std::mutex> lk(c->mu);
+   CU(cudaSetDevice(c->device));
+   if (!c->resident) return fail(c, SBQ_ERR_STATE, "sbq_solve before sbq_upload");
+   if (c->cfg.bias_mode != 0) return fail(c, SBQ_ERR_UNSUPPORTED, "bias_mode=1 is not implemented yet in this build");
+   DevParams& dp = c->dp;
+   dp.max_iter = c->cfg.max_iter;
+   dp.tol = c->cfg.theta_tol;
+   dp.row_eps = c->cfg.row_eps;
+   dp.min_frac = c->cfg.min_iso_frac;
+   dp.eff_len_norm = c->cfg.effective_len_norm;
+   dp.insert_mean = c->cfg.insert_mean;
+   dp.rpm = 1e6 / (double)(int)total_mapped_reads;   // total_mapped_reads() returns int (src/estimate.cpp:328)
+
+   cudaStream_t st = c->stream;
+   int64_t launches = 0;
+   CU(cudaEventRecord(c->ev[2], st));
+   CU(cudaEventRecord(c->ev_fork, st));
+   int used_side = 0;
+   // grid tier on the main stream first (it owns the whole GPU while it runs)
+   c->stats.grid_em_ms = 0;
+   if (!c->grid_list.empty()) {
+      CU(cudaEventRecord(c->ev[6], st));
+      int n_launch = 0;
+      int rc = grid_tier_launch(c->dp, c->d_lists_p + c->grid_list_off, (int)c->grid_list.size(), c->prop, &c->d_grid_scratch.p,
+                                &c->d_grid_scratch.cap, st, &n_launch);
+      if (rc != 0) return fail(c, rc, "grid tier launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      launches += n_launch;
+      CU(cudaEventRecord(c->ev[7], st));
+   }
+   for (auto& lc : c->classes) {
+      cudaStream_t ss = c->side[used_side % N_SIDE_STREAMS];
+      if (used_side < N_SIDE_STREAMS) CU(cudaStreamWaitEvent(ss, c->ev_fork, 0));
+      int rc = lc.lpr == 32 ? launch_cluster_class<32, 512>(c, lc, ss) : launch_cluster_class<8, 256>(c, lc, ss);
+      if (rc) return rc;
+      ++used_side;
+      ++launches;
+   }
+   if (!c->warp_list.empty()) {
+      const size_t smem = warp_tier_smem_bytes(c->warp_max_iso);
+      CU(cudaFuncSetAttribute(em_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int n = (int)c->warp_list.size();
+      em_warp_kernel<<<(n + WT_WARPS - 1) / WT_WARPS, WT_WARPS * 32, smem, st>>>(c->dp, c->d_lists_p + c->warp_list_off, n, c->warp_max_iso);
+      CU(cudaGetLastError());
+      ++launches;
+   }
+   for (int i = 0; i < std::min(used_side, N_SIDE_STREAMS); ++i) {
+      CU(cudaEventRecord(c->ev_join[i], c->side[i]));
+      CU(cudaStreamWaitEvent(st, c->ev_join[i], 0));
+   }
+   CU(cudaEventRecord(c->ev[3], st));
+   fpkm_sum_kernel<<<1, 1024, 0, st>>>(dp.locus_fpkm, c->n_loci, c->d_fpkm_sum);
+   CU(cudaGetLastError());
+   ++launches;
+   CU(cudaEventRecord(c->ev[4], st));
+   CU(cudaStreamSynchronize(st));
+   float ms = 0;
+   CU(cudaEventElapsedTime(&ms, c->ev[2], c->ev[4]));
+   c->stats.solve_ms = ms;
+   CU(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]));
+   c->stats.em_ms = ms;
+   if (!c->grid_list.empty()) {
+      CU(cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]));
+      c->stats.grid_em_ms = ms;
+   }
+   c->stats.kernel_launches = launches;
+   c->solved = true;
+   c->downloaded = false;
+   return SBQ_SUCCESS;
+}
+
+int sbq_fpkm_sum(sbq_ctx* c, double* local_sum) {
+   if (!c || !local_sum) return SBQ_ERR_INVALID;
+   std::lock_guard<std::mutex> lk(c->mu);
+   CU(cudaSetDevice(c->device));
+   if (!c->solved) return fail(c, SBQ_ERR_STATE, "sbq_fpkm_sum before sbq_solve");
+   CU(cudaMemcpyAsync(local_sum, c->d_fpkm_sum, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+   CU(cudaStreamSynchronize(c->stream));
+   return SBQ_SUCCESS;
+}
+
+int sbq_fpkm_sum_to_device(sbq_ctx* c, void* dev_double) {
+   if (!c || !dev_double) return SBQ_ERR_INVALID;
+   std::lock_guard<std::mutex> lk(c->mu);
+   CU(cudaSetDevice(c->device));
+   if (!c->solved) return fail(c, SBQ_ERR_STATE, "sbq_fpkm_sum_to_device before sbq_solve");
+   CU(cudaMemcpyAsync(dev_double, c->d_fpkm_sum, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+   CU(cudaStreamSynchronize(c->stream));
+   return SBQ_SUCCESS;
+}
+
+int sbq_finalize_tpm(sbq_ctx* c, double global_fpkm_sum) {
+   if (!c) return SBQ_ERR_INVALID;
+   std::lock_guard<std::mutex> lk(c->mu);
+   CU(cudaSetDevice(c->device));
+   if (!c->solved) return fail(c, SBQ_ERR_STATE, "sbq_finalize_tpm before sbq_solve");
+   const int64_t n = c->n_iso;
+   tpm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->dp.fpkm, c->d_tpm, n, global_fpkm_sum);
+   CU(cudaGetLastError());
+   c->stats.kernel_launches += 1;
+   c->downloaded = false;
+   return SBQ_SUCCESS;
+}
+
+int sbq_download(sbq_ctx* c) {
+   if (!c) return SBQ_ERR_INVALID;
+   std::lock_guard<std::mutex> lk(c->mu);
+   CU(cudaSetDevice(c->device));
+   if (!c->solved) return fail(c, SBQ_ERR_STATE, "sbq_download before sbq_solve");
+   const size_t ni = c->n_iso, nl = c->n_loci;
+   bool ok = c->r_theta.reserve(ni) && c->r_fpkm.reserve(ni) && c->r_frac.reserve(ni) && c->r_tpm.reserve(ni) &&
+             c->r_keep.reserve(ni) && c->r_iters.reserve(nl) && c->r_status.reserve(nl) && c->r_locus_fpkm.reserve(nl);
+   if (!ok) return fail(c, SBQ_ERR_NOMEM, "pinned result buffers");
+   cudaStream_t st = c->stream;
+   CU(cudaEventRecord(c->ev[8], st));
+   CU(cudaMemcpyAsync(c->r_theta.p, c->dp.theta, ni * 8, cudaMemcpyDeviceToHost, st));
+   CU(cudaMemcpyAsync(c->r_fpkm.p, c->dp.fpkm, ni * 8, cudaMemcpyDeviceToHost, st));
+   CU(cudaMemcpyAsync(c->r_frac.p, c->dp.frac, ni * 8, cudaMemcpyDeviceToHost, st));
+   CU(cudaMemcpyAsync(c->r_tpm.p, c->d_tpm, ni * 8, cudaMemcpyDeviceToHost, st));
+   CU(cudaMemcpyAsync(c->r_keep.p, c->dp.keep, ni * 4, cudaMemcpyDeviceToHost, st));
+   CU(cudaMemcpyAsync(c->r_iters.p, c->dp.iters, nl * 4, cudaMemcpyDeviceToHost, st));
+   CU(cudaMemcpyAsync(c->r_status.p, c->dp.status, nl * 4, cudaMemcpyDeviceToHost, st));
+   CU(cudaMemcpyAsync(&c->r_fpkm_sum, c->d_fpkm_sum, 8, cudaMemcpyDeviceToHost, st));
+   CU(cudaEventRecord(c->ev[9], st));
+   CU(cudaStreamSynchronize(st));
+   float ms = 0;
+   CU(cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]));
+   c->stats.download_ms = ms;
+   c->stats.d2h_bytes = (int64_t)ni * 36 + (int64_t)nl * 8 + 8;
+
+   // accounting for the metric: fragments*EM-iters and algorithmic bytes
+   const int64_t *lro = loc_row_off(c), *lio = loc_iso_off(c), *rp = row_ptr(c);
+   const int32_t* cnt = countp(c);
+   std::vector<char> is_grid(nl, 0);
+   for (int32_t l : c->grid_list) is_grid[l] = 1;
+   int64_t it_total = 0, frag_iters = 0, alg = 0, galg = 0;
+   const bool have_host = c->borrowed || c->h_row_ptr.n > 0;
+   for (size_t l = 0; l < nl && have_host; ++l) {
+      const int64_t it = c->r_iters.p[l];
+      const int64_t R = lro[l + 1] - lro[l], T = lio[l + 1] - lio[l], nz = rp[lro[l + 1]] - rp[lro[l]];
+      int64_t frags = 0;
+      for (int64_t i = lro[l]; i < lro[l + 1]; ++i) frags += cnt[i];
+      it_total += it;
+      frag_iters += frags * it;
+      const int64_t b = (12 * nz + 12 * R + 16 * T) * it;
+      alg += b;
+      if (is_grid[l]) galg += b;
+   }
+   c->stats.em_iters_total = it_total;
+   c->stats.frag_iters = frag_iters;
+   c->stats.alg_bytes = alg;
+   c->stats.grid_alg_bytes = galg;
+   c->downloaded = true;
+   return SBQ_SUCCESS;
+}
+
+int sbq_run(sbq_ctx* c, int64_t total_mapped_reads) {
+   int rc = sbq_upload(c);
+   if (rc) return rc;
+   if ((rc = sbq_solve(c, total_mapped_reads))) return rc;
+   double s = 0.0;
+   if ((rc = sbq_fpkm_sum(c, &s))) return rc;
+   if ((rc = sbq_finalize_tpm(c, s))) return rc;
+   return sbq_download(c);
+}
+
+int sbq_results(sbq_ctx* c, double* theta, double* fpkm, double* frac, double* tpm, int32_t* keep, int32_t* iters, int32_t* status) {
+   if (!c) return SBQ_ERR_INVALID;
+   std::lock_guard<std::mutex> lk(c->mu);
+   if (!c->downloaded) return fail(c, SBQ_ERR_STATE, "sbq_results before sbq_download / sbq_run");
+   const size_t ni = c->n_iso, nl = c->n_loci;
+   if (theta) memcpy(theta, c->r_theta.p, ni * 8);
+   if (fpkm) memcpy(fpkm, c->r_fpkm.p, ni * 8);
+   if (frac) memcpy(frac, c->r_frac.p, ni * 8);
+   if (tpm) memcpy(tpm, c->r_tpm.p, ni * 8);
+   if (keep) memcpy(keep, c->r_keep.p, ni * 4);
+   if (iters) memcpy(iters, c->r_iters.p, nl * 4);
+   if (status) memcpy(status, c->r_status.p, nl * 4);
+   return SBQ_SUCCESS;
+}
+
+int sbq_get_stats(const sbq_ctx* c, sbq_stats* out) {
+   if (!c || !out) return SBQ_ERR_INVALID;
+   *out = c->stats;
+   return SBQ_SUCCESS;
+}
+
+int sbq_em_solve(sbq_ctx* c, const sbq_locus* locus, double* theta, int32_t* iters) {
+   if (!c || !locus || !theta) return SBQ_ERR_INVALID;
+   int rc = sbq_clear(c);
+   if (rc) return rc;
+   if ((rc = sbq_submit(c, locus, 1))) return rc;
+   if ((rc = sbq_run(c, 1000000))) return rc;
+   int32_t it = 0, st = 0;
+   if ((rc = sbq_results(c, theta, nullptr, nullptr, nullptr, nullptr, &it, &st))) return rc;
+   if (iters) *iters = it;
+   return st;
+}
+
+// page-locked host memory for callers that want sbq_submit_flat to use their arrays in place
+void* sbq_host_alloc(size_t bytes) {
+   void* p = nullptr;
+   if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+   }
+   return p;
+}
+void sbq_host_free(void* p) {
+   if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,57 @@
+"""CPU: the C-ABI library loads, exports every symbol include/sbq.h declares, and refuses to compute
+without a device (no CPU fallback in the product)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "sbq.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sbq_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_symbols_all_exported(sbq_lib_path):
+    from strawberry_b200 import api
+    L = ctypes.CDLL(sbq_lib_path)
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/sbq.h but not exported by libsbq.so"
+    assert sorted(api.ABI_SYMBOLS) == declared
+
+
+def test_defaults_follow_the_reference(sbq_lib_path):
+    from strawberry_b200 import api
+    cfg = api.default_config()
+    assert cfg.max_iter == 1000          # include/estimate.hpp:236
+    assert cfg.theta_tol == 1e-2         # include/estimate.hpp:240
+    assert cfg.row_eps == 1e-5           # src/estimate.cpp:381
+    assert cfg.bias_mode == 0 and cfg.effective_len_norm == 0
+    assert api.lib().sbq_abi_version() == 1
+    assert b"no CUDA device" in api.lib().sbq_error_string(api.SBQ_ERR_NO_DEVICE)
+
+
+def test_no_device_means_error_not_fallback(sbq_lib_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    from strawberry_b200 import api
+    with pytest.raises(api.SbqError) as e:
+        api.Quantifier()
+    assert e.value.code == api.SBQ_ERR_NO_DEVICE
+
+
+def test_product_does_not_touch_the_oracle():
+    """The product package must never import / link oracle/."""
+    pkg = os.path.join(ROOT, "strawberry_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), f
+                assert "liboracle" not in text and "libsbref" not in text and "sbq_oracle" not in text, f

@@ -1,0 +1,161 @@
+"""GPU parity: the CUDA path (through the C ABI in include/sbq.h) against the CPU oracle on the same
+seeded inputs, against the reference's golden vectors, and - at full BASELINE size - through
+size-independent properties."""
+import numpy as np
+import pytest
+
+from strawberry_b200 import synth
+from util import assert_matches_oracle, load_golden, theta_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def q(sbq_lib_path):
+    from strawberry_b200 import api
+    qq = api.Quantifier()
+    yield qq
+    qq.close()
+
+
+def run_gpu(q, batch, tier=0, cluster=0, **cfg):
+    from strawberry_b200 import api
+    qq = q if not cfg else api.Quantifier(**cfg)
+    qq.clear()
+    qq.set_plan(tier, cluster)
+    qq.submit_flat(batch)
+    qq.validate()
+    qq.run(batch["total_mapped_reads"])
+    res = qq.results()
+    res["stats"] = qq.stats()
+    if cfg:
+        qq.close()
+    else:
+        qq.set_plan(0, 0)
+    return res
+
+
+def test_golden_vectors_from_the_reference(q, oracle_mod):
+    """theta against what the UNMODIFIED reference EmSolver returned (tests/golden/em_golden.npz)."""
+    b, theta_ref, rc_ref, iters, status = load_golden()
+    res = run_gpu(q, b)
+    assert np.array_equal(res["status"], status)
+    assert np.array_equal(res["iters"], iters)
+    ok, worst = theta_close(res["theta"], theta_ref, b)
+    assert ok.all(), worst
+
+
+@pytest.mark.parametrize("tier,cluster", [(0, 0), (1, 0), (2, 1), (2, 2), (2, 4), (2, 8), (2, 16), (3, 0)])
+def test_every_tier_matches_the_oracle(q, oracle_mod, tier, cluster):
+    b, *_ = load_golden()
+    ora = oracle_mod.quantify_batch(b, b["total_mapped_reads"])
+    res = run_gpu(q, b, tier, cluster)
+    assert_matches_oracle(res, ora, b, f"tier {tier} cluster {cluster}")
+    st = res["stats"]
+    if tier == 3:
+        assert st["loci_grid"] > 0
+    if tier == 2:
+        assert st["loci_cta"] > 0
+
+
+def test_human_shaped_sample_matches_oracle(q, oracle_mod):
+    b = synth.human_shaped(n_loci=2500, total_fragments=1_200_000, seed=31)
+    ora = oracle_mod.quantify_batch(b, b["total_mapped_reads"], n_threads=8)
+    res = run_gpu(q, b)
+    worst = assert_matches_oracle(res, ora, b, "human-shaped 2500 loci")
+    assert worst < 1e-6
+    assert res["stats"]["loci_warp"] > 0 and res["stats"]["loci_cta"] > 0
+    assert res["stats"]["frag_iters"] == int((np.add.reduceat(b["count"], b["loc_row_off"][:-1]).astype(np.int64) * ora["iters"]).sum())
+
+
+def test_filter_and_effective_length_epilogue(oracle_mod):
+    b = synth.human_shaped(n_loci=600, total_fragments=300_000, seed=41, max_rows=300)
+    b["iso_len"] = b["iso_len"].copy()
+    b["iso_len"][::17] = 150           # shorter than the insert mean -> "NA" branch (src/estimate.cpp:320-323)
+    kw = dict(min_iso_frac=0.01, effective_len_norm=1, insert_mean=200.0)
+    ora = oracle_mod.quantify_batch(b, b["total_mapped_reads"], min_iso_frac=0.01, effective_len_norm=True, insert_mean=200.0)
+    res = run_gpu(None, b, **kw)
+    assert_matches_oracle(res, ora, b, "epilogue")
+    assert (res["keep"] == 0).any() and (res["keep"] == 1).any()
+
+
+def test_giant_locus_grid_tier_matches_oracle(q, oracle_mod):
+    b = synth.giant(n_loci=2, rows_per_locus=60_000, seed=4)
+    ora = oracle_mod.quantify_batch(b, b["total_mapped_reads"], n_threads=2)
+    res = run_gpu(q, b)
+    assert res["stats"]["loci_grid"] == 2
+    assert_matches_oracle(res, ora, b, "giant grid tier")
+    # same loci through the cluster tier must give the same answer within the bar
+    res2 = run_gpu(q, b, 2, 16)
+    assert_matches_oracle(res2, ora, b, "giant through clusters")
+
+
+def test_submit_aos_equals_submit_flat(q):
+    b, *_ = load_golden()
+    flat = run_gpu(q, b)
+    q.clear()
+    L = len(b["loc_row_off"]) - 1
+    q.submit([synth.locus_slice(b, l) for l in range(L)])
+    q.run(b["total_mapped_reads"])
+    aos = q.results()
+    for k in ("theta", "fpkm", "frac", "tpm", "keep", "iters", "status"):
+        assert np.array_equal(flat[k], aos[k], equal_nan=True), k
+
+
+def test_solve_is_rerunnable_and_bit_reproducible(q):
+    b = synth.human_shaped(n_loci=1500, total_fragments=700_000, seed=51)
+    first = run_gpu(q, b)
+    q.solve(b["total_mapped_reads"])
+    q.finalize_tpm(q.fpkm_sum())
+    q.download()
+    again = q.results()
+    for k in ("theta", "fpkm", "frac", "tpm", "keep", "iters", "status"):
+        assert np.array_equal(first[k], again[k], equal_nan=True), k
+
+
+def test_em_solver_mirror_keeps_reference_semantics(q, oracle_mod):
+    from strawberry_b200 import api
+    rng = np.random.default_rng(3)
+    model = rng.random((40, 6)) * (rng.random((40, 6)) < 0.4) * 0.01
+    count = rng.integers(0, 50, 40)
+    em = api.EmSolver(q)
+    assert em.init(6, count, model) is True and em.run() is True       # src/estimate.cpp:366-488
+    st, th, it = oracle_mod.em_dense(count, model)
+    assert st == 0 and em.iters == it
+    assert np.allclose(em._theta, th, rtol=1e-9, atol=0)
+    em2 = api.EmSolver(q)
+    assert em2.init(2, [3, 4], np.full((2, 2), 5e-6)) is False and em2.run() is False   # init() false: no row > 1e-5
+    assert em2._theta == [3.5, 3.5]
+
+
+def test_full_size_config2_properties(q):
+    """BASELINE configs[1] at full size: 20k loci / 10M fragments. Oracle-free, size-independent checks."""
+    b = synth.human_shaped()
+    res = run_gpu(q, b)
+    assert res["stats"]["n_loci"] == 20000 and int(b["count"].sum()) == 10_000_000
+    lio = b["loc_iso_off"]
+    theta_sum = np.add.reduceat(res["theta"], lio[:-1])
+    # mass conservation for converged loci that advanced at least once
+    kept_row = np.maximum.reduceat((b["alpha"] > 1e-5).astype(np.int8), b["row_ptr"][:-1]) > 0
+    kept_cnt = np.add.reduceat(np.where(kept_row, b["count"], 0).astype(np.int64), b["loc_row_off"][:-1])
+    sel = (res["status"] == 0) & (res["iters"] > 1)
+    assert sel.sum() > 10000
+    rel = np.abs(theta_sum[sel] - kept_cnt[sel]) / np.maximum(kept_cnt[sel], 1)
+    assert rel.max() < 1e-9, rel.max()
+    # zero-denominator loci keep the uniform initial value total / T
+    tot = np.add.reduceat(b["count"].astype(np.int64), b["loc_row_off"][:-1])
+    for l in np.nonzero(res["status"] == 2)[0][:50]:
+        T = lio[l + 1] - lio[l]
+        assert np.array_equal(res["theta"][lio[l]:lio[l + 1]], np.full(T, tot[l] / T))
+    # per-locus fractions sum to one, TPM sums to 1e6 over the survivors
+    live = np.repeat(res["status"] != 3, np.diff(lio))
+    fsum = np.add.reduceat(np.where(live, res["frac"], 0.0), lio[:-1])
+    ok = (res["status"] != 3) & np.isfinite(fsum)
+    assert np.abs(fsum[ok] - 1.0).max() < 1e-9
+    assert abs(np.nansum(res["tpm"][res["keep"] != 0]) - 1e6) < 1e-3
+    # idempotence: a second solve of the resident batch is bit-identical
+    q.solve(b["total_mapped_reads"])
+    q.finalize_tpm(q.fpkm_sum())
+    q.download()
+    again = q.results()
+    assert np.array_equal(res["theta"], again["theta"]) and np.array_equal(res["iters"], again["iters"])
