@@ -155,6 +155,22 @@ int  sbq_results(sbq_ctx*, double* theta, double* fpkm, double* frac, double* tp
 
 int  sbq_get_stats(const sbq_ctx*, sbq_stats* out);
 
+/* One record per EM kernel launch of the last sbq_solve, timed with CUDA events on the stream the
+ * kernel was launched on (launches of different tiers overlap on separate streams). Byte / iteration
+ * accounting is filled in by sbq_download. Returns the number of records (may exceed cap). */
+typedef struct {
+   int32_t kind;            /* 1 = warp tier, 2 = cluster tier, 3 = grid (giant-locus) tier               */
+   int32_t cluster_size;    /* CTAs per locus (cluster tier)                                              */
+   int32_t lanes_per_row;
+   int32_t reserved;
+   int64_t n_loci, nnz;
+   double  ms;              /* kernel duration                                                            */
+   int64_t alg_bytes;       /* sum over its loci of (12 nnz + 12 R + 16 T) * iters                         */
+   int64_t frag_iters;
+   int64_t max_iters;       /* longest EM run among its loci (the launch's critical path)                 */
+} sbq_launch_stat;
+int  sbq_get_launch_stats(const sbq_ctx*, sbq_launch_stat* out, int cap);
+
 /* Single-locus convenience backing a drop-in EmSolver (EmSolver::init + run, src/estimate.cpp:366-488):
  * theta receives n_iso doubles; returns the sbq_locus_status (>= 0) or a negative sbq_error. */
 int  sbq_em_solve(sbq_ctx*, const sbq_locus* locus, double* theta, int32_t* iters);

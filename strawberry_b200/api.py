@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "sbq_abi_version", "sbq_error_string", "sbq_last_error", "sbq_config_default", "sbq_create", "sbq_destroy",
     "sbq_submit", "sbq_submit_flat", "sbq_clear", "sbq_validate", "sbq_host_alloc", "sbq_host_free",
     "sbq_upload", "sbq_solve", "sbq_download", "sbq_run", "sbq_fpkm_sum", "sbq_fpkm_sum_to_device",
-    "sbq_finalize_tpm", "sbq_results", "sbq_get_stats", "sbq_em_solve", "sbq_set_plan",
+    "sbq_finalize_tpm", "sbq_results", "sbq_get_stats", "sbq_get_launch_stats", "sbq_em_solve", "sbq_set_plan",
 ]
 
 
@@ -56,6 +56,12 @@ class Stats(ctypes.Structure):
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class LaunchStat(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("cluster_size", ctypes.c_int32), ("lanes_per_row", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("n_loci", ctypes.c_int64), ("nnz", ctypes.c_int64), ("ms", ctypes.c_double),
+                ("alg_bytes", ctypes.c_int64), ("frag_iters", ctypes.c_int64), ("max_iters", ctypes.c_int64)]
 
 
 _lib = None
@@ -89,6 +95,7 @@ def lib():
         L.sbq_finalize_tpm.argtypes = [ctypes.c_void_p, ctypes.c_double]
         L.sbq_results.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 7
         L.sbq_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(Stats)]
+        L.sbq_get_launch_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(LaunchStat), ctypes.c_int]
         L.sbq_em_solve.argtypes = [ctypes.c_void_p, ctypes.POINTER(Locus), ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32)]
         L.sbq_set_plan.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         _lib = L
@@ -216,6 +223,14 @@ class Quantifier:
         s = Stats()
         self._chk(self._L.sbq_get_stats(self._h, ctypes.byref(s)))
         return s.as_dict()
+
+    def launch_stats(self):
+        buf = (LaunchStat * 32)()
+        n = self._chk(self._L.sbq_get_launch_stats(self._h, buf, 32))
+        names = {1: "em_warp_kernel", 2: "em_cluster_kernel", 3: "em_grid_kernel"}
+        return [dict(kernel=names[buf[i].kind], cluster_size=buf[i].cluster_size, lanes_per_row=buf[i].lanes_per_row,
+                     n_loci=buf[i].n_loci, nnz=buf[i].nnz, ms=buf[i].ms, alg_bytes=buf[i].alg_bytes,
+                     frag_iters=buf[i].frag_iters, max_iters=buf[i].max_iters) for i in range(min(n, 32))]
 
     def results(self):
         st = self.stats()

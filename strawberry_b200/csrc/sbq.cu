@@ -84,6 +84,11 @@ struct LaunchClass {      // one kernel launch of the cluster tier
    size_t smem = 0;
 };
 
+struct LaunchTimer {      // CUDA events around one kernel launch, on the stream it is launched on
+   cudaEvent_t e0 = nullptr, e1 = nullptr;
+   bool used = false;
+};
+
 }  // namespace
 
 struct sbq_ctx {
@@ -94,6 +99,9 @@ struct sbq_ctx {
    cudaStream_t side[N_SIDE_STREAMS] = {};
    cudaEvent_t ev[10] = {};
    cudaEvent_t ev_fork = nullptr, ev_join[N_SIDE_STREAMS] = {};
+   LaunchTimer lt[N_SIDE_STREAMS + 2];          // [0] warp tier, [1] grid tier, [2+i] cluster class i
+   std::vector<sbq_launch_stat> launch_stats;   // filled by sbq_solve (+ bytes by sbq_download)
+   std::vector<int32_t> locus_launch;           // locus -> index into launch_stats
    std::mutex mu;
    std::string err;
 
@@ -385,6 +393,8 @@ int sbq_create(const sbq_config* cfg, sbq_ctx** out) {
    if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail(SBQ_ERR_CUDA);
    for (auto& e : c->ev_join)
       if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(SBQ_ERR_CUDA);
+   for (auto& t : c->lt)
+      if (cudaEventCreate(&t.e0) != cudaSuccess || cudaEventCreate(&t.e1) != cudaSuccess) return bail(SBQ_ERR_CUDA);
    *out = c;
    return SBQ_SUCCESS;
 }
@@ -402,6 +412,7 @@ void sbq_destroy(sbq_ctx* c) {
    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
    for (auto& e : c->ev_join) if (e) cudaEventDestroy(e);
+   for (auto& t : c->lt) { if (t.e0) cudaEventDestroy(t.e0); if (t.e1) cudaEventDestroy(t.e1); }
    for (auto& s : c->side) if (s) cudaStreamDestroy(s);
    if (c->stream) cudaStreamDestroy(c->stream);
    delete c;
@@ -412,9 +423,9 @@ int sbq_set_plan(sbq_ctx* c, int force_tier, int force_cluster) {
    if (force_tier < 0 || force_tier > 3) return fail(c, SBQ_ERR_INVALID, "force_tier must be 0..3");
    if (force_cluster != 0 && force_cluster != 1 && force_cluster != 2 && force_cluster != 4 && force_cluster != 8 && force_cluster != 16)
       return fail(c, SBQ_ERR_INVALID, "force_cluster must be 0, 1, 2, 4, 8 or 16");
+   if (c->force_tier != force_tier || c->force_cluster != force_cluster) c->resident = c->solved = c->downloaded = false;
    c->force_tier = force_tier;
    c->force_cluster = force_cluster;
-   c->resident = false;
    return SBQ_SUCCESS;
 }
 
@@ -611,6 +622,7 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
    int used_side = 0;
    // grid tier on the main stream first (it owns the whole GPU while it runs)
    c->stats.grid_em_ms = 0;
+   for (auto& t : c->lt) t.used = false;
    if (!c->grid_list.empty()) {
       CU(cudaEventRecord(c->ev[6], st));
       int n_launch = 0;
@@ -623,8 +635,12 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
    for (auto& lc : c->classes) {
       cudaStream_t ss = c->side[used_side % N_SIDE_STREAMS];
       if (used_side < N_SIDE_STREAMS) CU(cudaStreamWaitEvent(ss, c->ev_fork, 0));
+      LaunchTimer& t = c->lt[2 + used_side % N_SIDE_STREAMS];
+      CU(cudaEventRecord(t.e0, ss));
       int rc = lc.lpr == 32 ? launch_cluster_class<32, 512>(c, lc, ss) : launch_cluster_class<8, 256>(c, lc, ss);
       if (rc) return rc;
+      CU(cudaEventRecord(t.e1, ss));
+      t.used = true;
       ++used_side;
       ++launches;
    }
@@ -632,8 +648,11 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
       const size_t smem = warp_tier_smem_bytes(c->warp_max_iso);
       CU(cudaFuncSetAttribute(em_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       const int n = (int)c->warp_list.size();
+      CU(cudaEventRecord(c->lt[0].e0, st));
       em_warp_kernel<<<(n + WT_WARPS - 1) / WT_WARPS, WT_WARPS * 32, smem, st>>>(c->dp, c->d_lists_p + c->warp_list_off, n, c->warp_max_iso);
       CU(cudaGetLastError());
+      CU(cudaEventRecord(c->lt[0].e1, st));
+      c->lt[0].used = true;
       ++launches;
    }
    for (int i = 0; i < std::min(used_side, N_SIDE_STREAMS); ++i) {
@@ -654,6 +673,22 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
    if (!c->grid_list.empty()) {
       CU(cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]));
       c->stats.grid_em_ms = ms;
+   }
+   // per-launch records: [warp] [grid] [cluster classes...]
+   c->launch_stats.clear();
+   c->locus_launch.assign(c->n_loci, -1);
+   auto add_stat = [&](int kind, int cs, int lpr, const std::vector<int32_t>& loci, double ms_) {
+      sbq_launch_stat ls{};
+      ls.kind = kind; ls.cluster_size = cs; ls.lanes_per_row = lpr; ls.n_loci = (int64_t)loci.size(); ls.ms = ms_;
+      for (int32_t l : loci) c->locus_launch[l] = (int32_t)c->launch_stats.size();
+      c->launch_stats.push_back(ls);
+   };
+   if (c->lt[0].used) { CU(cudaEventElapsedTime(&ms, c->lt[0].e0, c->lt[0].e1)); add_stat(1, 1, 1, c->warp_list, ms); }
+   if (!c->grid_list.empty()) add_stat(3, 0, 32, c->grid_list, c->stats.grid_em_ms);
+   for (size_t i = 0; i < c->classes.size(); ++i) {
+      LaunchTimer& t = c->lt[2 + i % N_SIDE_STREAMS];
+      CU(cudaEventElapsedTime(&ms, t.e0, t.e1));
+      add_stat(2, c->classes[i].cs, c->classes[i].lpr, c->classes[i].loci, ms);
    }
    c->stats.kernel_launches = launches;
    c->solved = true;
@@ -727,6 +762,7 @@ int sbq_download(sbq_ctx* c) {
    for (int32_t l : c->grid_list) is_grid[l] = 1;
    int64_t it_total = 0, frag_iters = 0, alg = 0, galg = 0;
    const bool have_host = c->borrowed || c->h_row_ptr.n > 0;
+   for (auto& ls : c->launch_stats) ls.nnz = ls.alg_bytes = ls.frag_iters = ls.max_iters = 0;
    for (size_t l = 0; l < nl && have_host; ++l) {
       const int64_t it = c->r_iters.p[l];
       const int64_t R = lro[l + 1] - lro[l], T = lio[l + 1] - lio[l], nz = rp[lro[l + 1]] - rp[lro[l]];
@@ -737,6 +773,13 @@ int sbq_download(sbq_ctx* c) {
       const int64_t b = (12 * nz + 12 * R + 16 * T) * it;
       alg += b;
       if (is_grid[l]) galg += b;
+      const int32_t li = l < c->locus_launch.size() ? c->locus_launch[l] : -1;
+      if (li >= 0) {
+         c->launch_stats[li].nnz += nz;
+         c->launch_stats[li].alg_bytes += b;
+         c->launch_stats[li].frag_iters += frags * it;
+         c->launch_stats[li].max_iters = std::max<int64_t>(c->launch_stats[li].max_iters, it);
+      }
    }
    c->stats.em_iters_total = it_total;
    c->stats.frag_iters = frag_iters;
@@ -775,6 +818,13 @@ int sbq_get_stats(const sbq_ctx* c, sbq_stats* out) {
    if (!c || !out) return SBQ_ERR_INVALID;
    *out = c->stats;
    return SBQ_SUCCESS;
+}
+
+int sbq_get_launch_stats(const sbq_ctx* c, sbq_launch_stat* out, int cap) {
+   if (!c || (!out && cap > 0)) return SBQ_ERR_INVALID;
+   const int n = (int)c->launch_stats.size();
+   for (int i = 0; i < n && i < cap; ++i) out[i] = c->launch_stats[i];
+   return n;
 }
 
 int sbq_em_solve(sbq_ctx* c, const sbq_locus* locus, double* theta, int32_t* iters) {

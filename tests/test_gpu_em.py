@@ -30,8 +30,6 @@ def run_gpu(q, batch, tier=0, cluster=0, **cfg):
     res["stats"] = qq.stats()
     if cfg:
         qq.close()
-    else:
-        qq.set_plan(0, 0)
     return res
 
 
