@@ -23,7 +23,8 @@ def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS] + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("SBQ_NVCC_EXTRA", "").split()
+    cmd = [nvcc, *NVCC_FLAGS, *extra] + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     env = dict(os.environ)
     env.pop("CC", None), env.pop("CXX", None)   # this image exports a static-libstdc++ gcc wrapper; use /usr/bin/g++
     subprocess.check_call(cmd, env=env)

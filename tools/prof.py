@@ -1,0 +1,33 @@
+"""Small profiling driver (run under ncu on the GPU box):
+   python tools/prof.py giant [rows] [max_iter]   one giant locus through the grid tier
+   python tools/prof.py human [n_loci]            human-shaped batch through all tiers
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from strawberry_b200 import api, synth  # noqa: E402
+
+mode = sys.argv[1] if len(sys.argv) > 1 else "giant"
+if mode == "giant":
+    rows = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
+    max_iter = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+    b = synth.giant(n_loci=1, rows_per_locus=rows, seed=4)
+    q = api.Quantifier(max_iter=max_iter)
+else:
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
+    b = synth.human_shaped(n_loci=n, total_fragments=500 * n, seed=2)
+    q = api.Quantifier()
+q.submit_flat(b)
+q.upload()
+for _ in range(3):
+    q.solve(b["total_mapped_reads"])
+q.finalize_tpm(q.fpkm_sum())
+q.download()
+st = q.stats()
+print({k: st[k] for k in ("n_loci", "nnz", "solve_ms", "em_ms", "grid_em_ms", "em_iters_total", "alg_bytes", "grid_alg_bytes")})
+if st["grid_em_ms"] > 0:
+    print("grid GB/s", st["grid_alg_bytes"] / st["grid_em_ms"] / 1e6)
+for r in q.launch_stats():
+    print(r)
