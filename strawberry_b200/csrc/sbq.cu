@@ -80,6 +80,7 @@ struct LaunchClass {      // one kernel launch of the cluster tier
    int cs, lpr;
    std::vector<int32_t> loci;
    int max_iso = 0;
+   size_t max_slice = 0;  // estimated bytes of the largest per-CTA resident CSR slice
    size_t list_off = 0;   // offset into the device list buffer
    size_t smem = 0;
 };
@@ -213,8 +214,10 @@ int ensure_origin(sbq_ctx* c) {
 }
 
 template <int LPR, int NT>
-size_t cluster_class_smem(int max_iso) {
-   size_t want = ((size_t)5 * max_iso + 8 + (size_t)(NT / LPR) * max_iso) * sizeof(double);
+size_t cluster_class_smem(int max_iso, size_t slice_bytes) {
+   // fixed part + full set of group accumulators + the (estimated) largest resident CSR slice of the class
+   size_t fixed = ((size_t)5 * max_iso + 8 + (size_t)(NT / LPR) * max_iso) * sizeof(double);
+   size_t want = std::max(2 * fixed, fixed + slice_bytes + 1024);
    return std::min(want, SMEM_CAP);
 }
 
@@ -263,11 +266,14 @@ int plan(sbq_ctx* c) {
          int lpr = (R > 0 && nnz / R >= 12) ? 32 : 8;
          int li = lpr == 32 ? 1 : 0;
          if (!slot[csi][li]) {
-            tmp.push_back(LaunchClass{cs, lpr, {}, 0, 0, 0});
+            tmp.push_back(LaunchClass{cs, lpr, {}, 0, 0, 0, 0});
             slot[csi][li] = &tmp.back();
          }
          slot[csi][li]->loci.push_back((int32_t)l);
          slot[csi][li]->max_iso = std::max(slot[csi][li]->max_iso, (int)T);
+         // per-CTA slice: 10 B per non-zero + 8 B per row, 15 % slack for the row-granular split
+         const size_t slice = (size_t)((double)(10 * nnz + 8 * R) / cs * 1.15) + 64 * (size_t)T / 4 + 256;
+         slot[csi][li]->max_slice = std::max(slot[csi][li]->max_slice, slice);
       }
    }
    auto by_size = [&](int32_t a, int32_t b) { return nnz_of[a] != nnz_of[b] ? nnz_of[a] > nnz_of[b] : a < b; };
@@ -275,7 +281,7 @@ int plan(sbq_ctx* c) {
    std::sort(c->grid_list.begin(), c->grid_list.end(), by_size);
    for (auto& lc : tmp) {
       std::sort(lc.loci.begin(), lc.loci.end(), by_size);
-      lc.smem = lc.lpr == 32 ? cluster_class_smem<32, 512>(lc.max_iso) : cluster_class_smem<8, 256>(lc.max_iso);
+      lc.smem = lc.lpr == 32 ? cluster_class_smem<32, 512>(lc.max_iso, lc.max_slice) : cluster_class_smem<8, 256>(lc.max_iso, lc.max_slice);
       int G = lc.lpr == 32 ? cluster_groups_for<32, 512>(lc.max_iso, lc.smem) : cluster_groups_for<8, 256>(lc.max_iso, lc.smem);
       if (G <= 0) return fail(c, SBQ_ERR_UNSUPPORTED, "locus with %d isoforms does not fit the cluster tier", lc.max_iso);
       c->classes.push_back(std::move(lc));
@@ -632,9 +638,10 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
       launches += n_launch;
       CU(cudaEventRecord(c->ev[7], st));
    }
+   const bool serialize = getenv("SBQ_SERIALIZE") != nullptr;   // debugging / profiling: one stream, isolated kernel times
    for (auto& lc : c->classes) {
-      cudaStream_t ss = c->side[used_side % N_SIDE_STREAMS];
-      if (used_side < N_SIDE_STREAMS) CU(cudaStreamWaitEvent(ss, c->ev_fork, 0));
+      cudaStream_t ss = serialize ? st : c->side[used_side % N_SIDE_STREAMS];
+      if (!serialize && used_side < N_SIDE_STREAMS) CU(cudaStreamWaitEvent(ss, c->ev_fork, 0));
       LaunchTimer& t = c->lt[2 + used_side % N_SIDE_STREAMS];
       CU(cudaEventRecord(t.e0, ss));
       int rc = lc.lpr == 32 ? launch_cluster_class<32, 512>(c, lc, ss) : launch_cluster_class<8, 256>(c, lc, ss);
@@ -655,7 +662,7 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
       c->lt[0].used = true;
       ++launches;
    }
-   for (int i = 0; i < std::min(used_side, N_SIDE_STREAMS); ++i) {
+   for (int i = 0; i < std::min(used_side, N_SIDE_STREAMS) && !serialize; ++i) {
       CU(cudaEventRecord(c->ev_join[i], c->side[i]));
       CU(cudaStreamWaitEvent(st, c->ev_join[i], 0));
    }

@@ -227,18 +227,20 @@ em_warp_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, int ma
 // row pass -> fixed-order sum over groups -> partial theta' exchanged through distributed shared
 // memory (one cluster barrier, double-buffered) -> every CTA forms the same theta' and norm.
 // --------------------------------------------------------------------------------------------
-struct ClusterSmemLayout {
-   int T, G;
-   __host__ __device__ size_t doubles() const { return (size_t)3 * T + 2 * ((size_t)T + 4) + (size_t)G * T; }
-};
-
 template <int LPR, int NT>
 __host__ __device__ inline int cluster_groups_for(int T, size_t smem_bytes) {
-   const long long budget = (long long)(smem_bytes / sizeof(double)) - 5LL * T - 8;
+   // accumulators may take at most half of the dynamic shared memory; the rest is for the resident CSR slice
+   const long long budget = (long long)(smem_bytes / 2 / sizeof(double)) - 5LL * T - 8;
    long long G = budget / (T > 0 ? T : 1);
    const int per_warp = 32 / LPR;
    if (G > NT / LPR) G = NT / LPR;
    G = (G / per_warp) * per_warp;
+   if (G < per_warp) {   // large T: let the accumulators use all of it (streaming mode)
+      const long long full = (long long)(smem_bytes / sizeof(double)) - 5LL * T - 8;
+      G = full / (T > 0 ? T : 1);
+      if (G > NT / LPR) G = NT / LPR;
+      G = (G / per_warp) * per_warp;
+   }
    return (int)G;   // 0 => does not fit
 }
 
@@ -253,6 +255,85 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
    for (int w = 0; w < NT / 32; ++w) t += red[w];
    __syncthreads();
    return t;
+}
+
+// Row accessors of one CTA's slice: streamed from global/L2, or resident in shared memory.
+struct GlobalRows {
+   const int64_t* rp;      // row_ptr of the slice's first row
+   const double* al;       // alpha + k_a
+   const int32_t* col;     // col + k_a
+   int32_t* ne;            // neff of the slice's first row
+   int64_t k_a;
+   __device__ __forceinline__ unsigned start(int i) const { return (unsigned)(rp[i] - k_a); }
+   __device__ __forceinline__ double a(unsigned k) const { return al[k]; }
+   __device__ __forceinline__ int c(unsigned k) const { return col[k]; }
+   __device__ __forceinline__ int get_ne(int i) const { return ne[i]; }
+   __device__ __forceinline__ void set_ne(int i, int v) const { ne[i] = v; }
+};
+struct SmemRows {
+   const unsigned* rp;
+   const double* al;
+   const unsigned short* col;
+   int* ne;
+   __device__ __forceinline__ unsigned start(int i) const { return rp[i]; }
+   __device__ __forceinline__ double a(unsigned k) const { return al[k]; }
+   __device__ __forceinline__ int c(unsigned k) const { return col[k]; }
+   __device__ __forceinline__ int get_ne(int i) const { return ne[i]; }
+   __device__ __forceinline__ void set_ne(int i, int v) const { ne[i] = v; }
+};
+
+// Setup pass over the CTA's rows: total count, row filter (-> ne), column sums of the kept rows.
+template <int LPR, typename Rows>
+__device__ __forceinline__ void cluster_setup_pass(const Rows& rows, const int32_t* __restrict__ cnt, int nrows, int G, int g, int lg,
+                                                   double row_eps, double* my_acc, long long& tot, int& kept) {
+   for (int base = 0; base < nrows; base += G) {
+      const int i = base + g;
+      const bool valid = i < nrows;
+      unsigned k0 = 0, k1 = 0;
+      int n = 0;
+      if (valid) { k0 = rows.start(i); k1 = rows.start(i + 1); n = cnt[i]; }
+      bool keep = false;
+      for (unsigned k = k0 + lg; k < k1; k += LPR) keep |= rows.a(k) > row_eps;
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) keep |= (bool)__shfl_xor_sync(0xffffffffu, (int)keep, o);
+      if (valid && lg == 0) { rows.set_ne(i, keep ? n : -1); tot += n; kept += keep; }
+      if (keep)
+         for (unsigned k = k0 + lg; k < k1; k += LPR) my_acc[rows.c(k)] += rows.a(k);
+   }
+}
+
+// One E/M pass over the CTA's rows with the scaled theta in th[]; two rows per group in flight.
+template <int LPR, typename Rows>
+__device__ __forceinline__ void cluster_em_pass(const Rows& rows, int nrows, int G, int g, int lg, const double* th, double* my_acc, int& zero) {
+   for (int base = 0; base < nrows; base += 2 * G) {
+      const int i0 = base + g, i1 = base + G + g;
+      int ne0 = -1, ne1 = -1;
+      unsigned a0 = 0, b0 = 0, a1 = 0, b1 = 0;
+      if (i0 < nrows) { ne0 = rows.get_ne(i0); if (ne0 >= 0) { a0 = rows.start(i0); b0 = rows.start(i0 + 1); } }
+      if (i1 < nrows) { ne1 = rows.get_ne(i1); if (ne1 >= 0) { a1 = rows.start(i1); b1 = rows.start(i1 + 1); } }
+      double d0 = 0.0, d1 = 0.0;
+      for (unsigned k = a0 + lg; k < b0; k += LPR) d0 += rows.a(k) * th[rows.c(k)];
+      for (unsigned k = a1 + lg; k < b1; k += LPR) d1 += rows.a(k) * th[rows.c(k)];
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) {
+         d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+         d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+      }
+      if (ne0 >= 0) {
+         if (d0 == 0) zero = 1;
+         else {
+            const double r = (double)ne0 / d0;
+            for (unsigned k = a0 + lg; k < b0; k += LPR) { const int c = rows.c(k); my_acc[c] += rows.a(k) * th[c] * r; }
+         }
+      }
+      if (ne1 >= 0) {
+         if (d1 == 0) zero = 1;
+         else {
+            const double r = (double)ne1 / d1;
+            for (unsigned k = a1 + lg; k < b1; k += LPR) { const int c = rows.c(k); my_acc[c] += rows.a(k) * th[c] * r; }
+         }
+      }
+   }
 }
 
 template <int LPR, int NT>
@@ -277,13 +358,11 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
    double* sdiv = cur + T;             // [T] column sums s_j of the kept rows
    double* part = sdiv + T;            // [2][T+4] exchange buffers: partial theta', flag, total, kept
    double* acc = part + 2 * (T + 4);   // [G][T] group-private accumulators
+   double* res = acc + (size_t)G * T;  // resident CSR slice (if it fits)
    __shared__ double red[NT / 32];
    __shared__ int s_rows[2];
 
    const int64_t* __restrict__ rp = p.row_ptr + r0;
-   const int32_t* __restrict__ col = p.col;
-   const double* __restrict__ al = p.alpha;
-   int32_t* neff = p.neff + r0;
 
    // rows of this CTA: split by non-zeros (lower_bound on row_ptr)
    if (tid < 2) {
@@ -300,29 +379,35 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
    }
    for (int x = tid; x < G * T; x += NT) acc[x] = 0.0;
    __syncthreads();
-   const int ra = s_rows[0], rb = s_rows[1];
+   const int ra = s_rows[0], rb = s_rows[1], nrows = rb - ra;
+   const int64_t k_a = rp[ra];
+   const unsigned nnz_c = (unsigned)(rp[rb] - k_a);
    const int g = tid / LPR, lg = tid % LPR;
    const bool active = g < G;
    double* my_acc = acc + (size_t)(active ? g : 0) * T;
+
+   // resident slice: alpha f64 | row starts u32 | ne i32 | col u16
+   const size_t used = (size_t)((char*)res - (char*)smem);
+   const size_t need = (size_t)nnz_c * 8 + ((size_t)nrows + 1) * 4 + (size_t)nrows * 4 + (size_t)nnz_c * 2 + 32;
+   const bool resident = used + need <= smem_bytes;
+   double* s_al = res;
+   unsigned* s_rp = (unsigned*)(s_al + nnz_c);
+   int* s_ne = (int*)(s_rp + nrows + 1);
+   unsigned short* s_col = (unsigned short*)(s_ne + nrows);
+   GlobalRows grows{rp + ra, p.alpha + k_a, p.col + k_a, p.neff + r0 + ra, k_a};
+   SmemRows srows{s_rp, s_al, s_col, s_ne};
+   if (resident) {
+      for (unsigned k = tid; k < nnz_c; k += NT) { s_al[k] = grows.al[k]; s_col[k] = (unsigned short)grows.col[k]; }
+      for (int i = tid; i <= nrows; i += NT) s_rp[i] = (unsigned)(rp[ra + i] - k_a);
+      __syncthreads();
+   }
 
    // ---- setup pass: total, row filter, column sums
    long long tot = 0;
    int kept = 0;
    if (active) {
-      for (int base_row = ra; base_row < rb; base_row += G) {
-         const int i = base_row + g;
-         const bool valid = i < rb;
-         int64_t k0 = 0, k1 = 0;
-         int n = 0;
-         if (valid) { k0 = rp[i]; k1 = rp[i + 1]; n = p.count[r0 + i]; }
-         bool keep = false;
-         for (int64_t k = k0 + lg; k < k1; k += LPR) keep |= al[k] > p.row_eps;
-#pragma unroll
-         for (int o = LPR / 2; o > 0; o >>= 1) keep |= (bool)__shfl_xor_sync(0xffffffffu, (int)keep, o);
-         if (valid && lg == 0) { neff[i] = keep ? n : -1; tot += n; kept += keep; }
-         if (keep)
-            for (int64_t k = k0 + lg; k < k1; k += LPR) my_acc[col[k]] += al[k];
-      }
+      if (resident) cluster_setup_pass<LPR>(srows, p.count + r0 + ra, nrows, G, g, lg, p.row_eps, my_acc, tot, kept);
+      else cluster_setup_pass<LPR>(grows, p.count + r0 + ra, nrows, G, g, lg, p.row_eps, my_acc, tot, kept);
    }
    __syncthreads();
    {
@@ -363,29 +448,8 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
          double* pb = part + (size_t)(it & 1) * (T + 4);
          int zero = 0;
          if (active) {
-            for (int base_row = ra; base_row < rb; base_row += G) {
-               const int i = base_row + g;
-               int ne = -1;
-               int64_t k0 = 0, k1 = 0;
-               if (i < rb) {
-                  ne = neff[i];
-                  if (ne >= 0) { k0 = rp[i]; k1 = rp[i + 1]; }
-               }
-               double d = 0.0;
-               for (int64_t k = k0 + lg; k < k1; k += LPR) d += al[k] * th[col[k]];
-               d = group_sum<LPR>(d);
-               if (ne >= 0) {
-                  if (d == 0) {
-                     zero = 1;
-                  } else {
-                     const double r = (double)ne / d;
-                     for (int64_t k = k0 + lg; k < k1; k += LPR) {
-                        const int c = col[k];
-                        my_acc[c] += al[k] * th[c] * r;
-                     }
-                  }
-               }
-            }
+            if (resident) cluster_em_pass<LPR>(srows, nrows, G, g, lg, th, my_acc, zero);
+            else cluster_em_pass<LPR>(grows, nrows, G, g, lg, th, my_acc, zero);
          }
          zero = __syncthreads_or(zero);
          for (int j = tid; j < T; j += NT) {

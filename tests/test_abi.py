@@ -9,8 +9,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    src = open(os.path.join(ROOT, "include", "sbq.h")).read()
+def _declared_symbols(header="sbq.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(sbq_[a-z_0-9]+)\s*\(", src)))
 
@@ -23,6 +23,11 @@ def test_header_symbols_all_exported(sbq_lib_path):
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/sbq.h but not exported by libsbq.so"
     assert sorted(api.ABI_SYMBOLS) == declared
+    from strawberry_b200 import builder
+    declared_b = _declared_symbols("sbq_builder.h")
+    for name in declared_b:
+        assert hasattr(L, name), f"{name} declared in include/sbq_builder.h but not exported by libsbq.so"
+    assert sorted(builder.BUILDER_SYMBOLS) == declared_b
 
 
 def test_defaults_follow_the_reference(sbq_lib_path):
