@@ -1,0 +1,78 @@
+"""CPU: the multi-GPU host logic (partition + the single all-reduce) with world_size 2 on gloo. The per-rank
+solver is a stand-in (the CPU oracle) because the product has no CPU path; what is under test is the plumbing."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from strawberry_b200 import partition, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_lpt_partition_is_balanced_and_deterministic():
+    b = synth.human_shaped(n_loci=3000, total_fragments=1_000_000, seed=8)
+    cost = partition.locus_cost(b)
+    for n in (2, 4, 8):
+        parts = partition.lpt_partition(cost, n)
+        assert sorted(np.concatenate(parts).tolist()) == list(range(3000))
+        loads = np.array([cost[p].sum() for p in parts])
+        assert loads.max() <= max(cost.max(), 1.02 * loads.mean())      # LPT bound: the heaviest locus or near-even
+        again = partition.lpt_partition(cost, n)
+        assert all(np.array_equal(a, c) for a, c in zip(parts, again))
+
+
+def test_take_preserves_loci():
+    b = synth.human_shaped(n_loci=200, total_fragments=50_000, seed=9)
+    idx = np.array([3, 17, 18, 150, 199])
+    sub, isos = partition.take(b, idx)
+    for k, l in enumerate(idx):
+        a, c = synth.locus_slice(b, l), synth.locus_slice(sub, k)
+        assert a[0] == c[0]
+        for x, y in zip(a[1:], c[1:]):
+            assert np.array_equal(x, y)
+    assert np.array_equal(isos, np.concatenate([np.arange(b["loc_iso_off"][l], b["loc_iso_off"][l + 1]) for l in idx]))
+
+
+class OracleLocal:
+    """test stand-in for GpuLocal"""
+
+    def solve(self, batch, total_mapped_reads):
+        import oracle
+        self.r = oracle.quantify_batch(batch, total_mapped_reads, min_iso_frac=0.01)
+        return float(self.r["fpkm"][self.r["keep"] != 0].sum())
+
+    def finalize(self, s):
+        self.r["tpm"] = 1e6 * self.r["fpkm"] / s
+        return self.r
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    b = synth.human_shaped(n_loci=400, total_fragments=200_000, seed=12, max_rows=300)
+    full = partition.quantify_distributed(b, b["total_mapped_reads"], OracleLocal())
+    if rank == 0:
+        np.savez(out, **{k: v for k, v in full.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_matches_single_process(tmp_path):
+    import oracle
+    out = str(tmp_path / "dist.npz")
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got = np.load(out)
+    b = synth.human_shaped(n_loci=400, total_fragments=200_000, seed=12, max_rows=300)
+    ref = oracle.quantify_batch(b, b["total_mapped_reads"], min_iso_frac=0.01)
+    for k in ("theta", "fpkm", "frac", "keep", "iters", "status"):
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
+    # TPM differs only by the order of the FPKM sum (per-rank partial sums vs one sequential sum)
+    assert np.allclose(got["tpm"], ref["tpm"], rtol=1e-12, equal_nan=True)
+    assert abs(np.nansum(got["tpm"][got["keep"] != 0]) - 1e6) < 1e-3
