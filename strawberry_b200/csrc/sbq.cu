@@ -213,19 +213,19 @@ int ensure_origin(sbq_ctx* c) {
    return SBQ_SUCCESS;
 }
 
-template <int LPR, int NT>
 size_t cluster_class_smem(int max_iso, size_t slice_bytes) {
-   // fixed part + full set of group accumulators + the (estimated) largest resident CSR slice of the class
-   size_t fixed = ((size_t)5 * max_iso + 8 + (size_t)(NT / LPR) * max_iso) * sizeof(double);
-   size_t want = std::max(2 * fixed, fixed + slice_bytes + 1024);
-   return std::min(want, SMEM_CAP);
+   // fixed arrays + the larger of (estimated largest resident slice, a full set of streaming accumulators)
+   const size_t fixed = cluster_fixed_doubles(max_iso) * sizeof(double);
+   const size_t stream = (size_t)(CL_NT / CL_LPR_STREAM) * max_iso * sizeof(double);
+   return std::min(fixed + std::max(slice_bytes, stream) + 256, SMEM_CAP);
 }
 
 int cluster_size_for(int64_t nnz) {
-   if (nnz <= 6 * 1024) return 1;
-   if (nnz <= 16 * 1024) return 2;
-   if (nnz <= 40 * 1024) return 4;
-   if (nnz <= 100 * 1024) return 8;
+   // ~14 B of shared memory per non-zero (CSR + CSC index): keep a CTA's slice under ~10k non-zeros
+   if (nnz <= 9 * 1024) return 1;
+   if (nnz <= 18 * 1024) return 2;
+   if (nnz <= 36 * 1024) return 4;
+   if (nnz <= 72 * 1024) return 8;
    return 16;
 }
 
@@ -239,9 +239,9 @@ int plan(sbq_ctx* c) {
    c->classes.clear();
    c->warp_max_iso = 1;
    std::vector<int64_t> nnz_of(c->n_loci);
-   LaunchClass* slot[5][2] = {};
+   LaunchClass* slot[5] = {};
    std::vector<LaunchClass> tmp;
-   tmp.reserve(10);
+   tmp.reserve(5);
    const int64_t grid_min_nnz = 2 * 1000 * 1000;
    for (int64_t l = 0; l < c->n_loci; ++l) {
       const int64_t R = lro[l + 1] - lro[l], T = lio[l + 1] - lio[l];
@@ -250,7 +250,7 @@ int plan(sbq_ctx* c) {
       if (T > SBQ_MAX_ISO) return fail(c, SBQ_ERR_UNSUPPORTED, "locus %lld has %lld isoforms (> SBQ_MAX_ISO)", (long long)l, (long long)T);
       int tier;
       if (c->force_tier) tier = c->force_tier;
-      else if (T <= WT_MAX_ISO && nnz <= 2048) tier = 1;
+      else if (T <= WT_MAX_ISO && R <= 32 && nnz <= 4 * R + 32) tier = 1;   // one row per lane, rows mostly register-resident
       else if (nnz >= grid_min_nnz) tier = 3;
       else tier = 2;
       if (tier == 1 && T > WT_MAX_ISO) tier = 2;
@@ -263,17 +263,15 @@ int plan(sbq_ctx* c) {
       } else {
          int cs = c->force_cluster ? c->force_cluster : cluster_size_for(nnz);
          int csi = cs == 1 ? 0 : cs == 2 ? 1 : cs == 4 ? 2 : cs == 8 ? 3 : 4;
-         int lpr = (R > 0 && nnz / R >= 12) ? 32 : 8;
-         int li = lpr == 32 ? 1 : 0;
-         if (!slot[csi][li]) {
-            tmp.push_back(LaunchClass{cs, lpr, {}, 0, 0, 0, 0});
-            slot[csi][li] = &tmp.back();
+         if (!slot[csi]) {
+            tmp.push_back(LaunchClass{cs, 0, {}, 0, 0, 0, 0});
+            slot[csi] = &tmp.back();
          }
-         slot[csi][li]->loci.push_back((int32_t)l);
-         slot[csi][li]->max_iso = std::max(slot[csi][li]->max_iso, (int)T);
-         // per-CTA slice: 10 B per non-zero + 8 B per row, 15 % slack for the row-granular split
-         const size_t slice = (size_t)((double)(10 * nnz + 8 * R) / cs * 1.15) + 64 * (size_t)T / 4 + 256;
-         slot[csi][li]->max_slice = std::max(slot[csi][li]->max_slice, slice);
+         slot[csi]->loci.push_back((int32_t)l);
+         slot[csi]->max_iso = std::max(slot[csi]->max_iso, (int)T);
+         // per-CTA resident slice with 15 % slack for the row-granular split
+         const size_t slice = (size_t)(1.12 * (double)cluster_resident_bytes((size_t)(nnz / cs + 1), (size_t)(R / cs + 1), (int)T)) + 512;
+         slot[csi]->max_slice = std::max(slot[csi]->max_slice, slice);
       }
    }
    auto by_size = [&](int32_t a, int32_t b) { return nnz_of[a] != nnz_of[b] ? nnz_of[a] > nnz_of[b] : a < b; };
@@ -281,9 +279,9 @@ int plan(sbq_ctx* c) {
    std::sort(c->grid_list.begin(), c->grid_list.end(), by_size);
    for (auto& lc : tmp) {
       std::sort(lc.loci.begin(), lc.loci.end(), by_size);
-      lc.smem = lc.lpr == 32 ? cluster_class_smem<32, 512>(lc.max_iso, lc.max_slice) : cluster_class_smem<8, 256>(lc.max_iso, lc.max_slice);
-      int G = lc.lpr == 32 ? cluster_groups_for<32, 512>(lc.max_iso, lc.smem) : cluster_groups_for<8, 256>(lc.max_iso, lc.smem);
-      if (G <= 0) return fail(c, SBQ_ERR_UNSUPPORTED, "locus with %d isoforms does not fit the cluster tier", lc.max_iso);
+      lc.smem = cluster_class_smem(lc.max_iso, lc.max_slice);
+      if (cluster_stream_groups(lc.max_iso, lc.smem) <= 0)
+         return fail(c, SBQ_ERR_UNSUPPORTED, "locus with %d isoforms does not fit the cluster tier", lc.max_iso);
       c->classes.push_back(std::move(lc));
    }
    // biggest clusters first: they sit on the critical path
@@ -313,9 +311,9 @@ int set_kernel_attrs(sbq_ctx* c, K kernel, size_t smem, bool nonportable) {
    return SBQ_SUCCESS;
 }
 
-template <int LPR, int NT>
 int launch_cluster_class(sbq_ctx* c, const LaunchClass& lc, cudaStream_t st) {
-   auto kernel = em_cluster_kernel<LPR, NT>;
+   constexpr int NT = CL_NT;
+   auto kernel = em_cluster_kernel<CL_NT>;
    int rc = set_kernel_attrs(c, kernel, lc.smem, lc.cs > 8);
    if (rc) return rc;
    cudaLaunchConfig_t cfg{};
@@ -550,7 +548,8 @@ int sbq_upload(sbq_ctx* c) {
    const size_t sz_lro = align_up((c->n_loci + 1) * sizeof(int64_t)), sz_rp = align_up((c->n_row + 1) * sizeof(int64_t));
    const size_t sz_col = align_up(c->nnz * sizeof(int32_t)), sz_al = align_up(c->nnz * sizeof(double));
    const size_t sz_cnt = align_up(c->n_row * sizeof(int32_t)), sz_il = align_up(c->n_iso * sizeof(int32_t));
-   const size_t in_bytes = 2 * sz_lro + sz_rp + sz_col + sz_al + 2 * sz_cnt + sz_il;
+   const size_t sz_csc = align_up(c->nnz * 4 + 16);
+   const size_t in_bytes = 2 * sz_lro + sz_rp + sz_col + sz_al + 2 * sz_cnt + sz_il + sz_csc;
    const size_t sz_iso_d = align_up(c->n_iso * sizeof(double)), sz_iso_i = align_up(c->n_iso * sizeof(int32_t));
    const size_t sz_loc_i = align_up(c->n_loci * sizeof(int32_t)), sz_loc_d = align_up(c->n_loci * sizeof(double));
    const size_t out_bytes = 4 * sz_iso_d + sz_iso_i + 2 * sz_loc_i + sz_loc_d + 256;
@@ -568,6 +567,7 @@ int sbq_upload(sbq_ctx* c) {
    int32_t* d_cnt = (int32_t*)carve(sz_cnt);
    dp.neff = (int32_t*)carve(sz_cnt);
    int32_t* d_il = (int32_t*)carve(sz_il);
+   dp.csc = (unsigned*)carve(sz_csc);
    dp.loc_row_off = d_lro; dp.loc_iso_off = d_lio; dp.row_ptr = d_rp; dp.col = d_col; dp.alpha = d_al;
    dp.count = d_cnt; dp.iso_len = d_il;
    p = (char*)c->d_out.p;
@@ -644,7 +644,7 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
       if (!serialize && used_side < N_SIDE_STREAMS) CU(cudaStreamWaitEvent(ss, c->ev_fork, 0));
       LaunchTimer& t = c->lt[2 + used_side % N_SIDE_STREAMS];
       CU(cudaEventRecord(t.e0, ss));
-      int rc = lc.lpr == 32 ? launch_cluster_class<32, 512>(c, lc, ss) : launch_cluster_class<8, 256>(c, lc, ss);
+      int rc = launch_cluster_class(c, lc, ss);
       if (rc) return rc;
       CU(cudaEventRecord(t.e1, ss));
       t.used = true;
@@ -655,8 +655,13 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
       const size_t smem = warp_tier_smem_bytes(c->warp_max_iso);
       CU(cudaFuncSetAttribute(em_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       const int n = (int)c->warp_list.size();
+      int per_sm = 1;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_warp_kernel, WT_WARPS * 32, smem));
+      const int grid = std::max(1, std::min((n + WT_WARPS - 1) / WT_WARPS, per_sm * c->prop.multiProcessorCount));
+      int* queue = (int*)((char*)c->d_fpkm_sum + 64);
+      CU(cudaMemsetAsync(queue, 0, sizeof(int), st));
       CU(cudaEventRecord(c->lt[0].e0, st));
-      em_warp_kernel<<<(n + WT_WARPS - 1) / WT_WARPS, WT_WARPS * 32, smem, st>>>(c->dp, c->d_lists_p + c->warp_list_off, n, c->warp_max_iso);
+      em_warp_kernel<<<grid, WT_WARPS * 32, smem, st>>>(c->dp, c->d_lists_p + c->warp_list_off, n, c->warp_max_iso, queue);
       CU(cudaGetLastError());
       CU(cudaEventRecord(c->lt[0].e1, st));
       c->lt[0].used = true;
@@ -695,7 +700,7 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
    for (size_t i = 0; i < c->classes.size(); ++i) {
       LaunchTimer& t = c->lt[2 + i % N_SIDE_STREAMS];
       CU(cudaEventElapsedTime(&ms, t.e0, t.e1));
-      add_stat(2, c->classes[i].cs, c->classes[i].lpr, c->classes[i].loci, ms);
+      add_stat(2, c->classes[i].cs, 0, c->classes[i].loci, ms);
    }
    c->stats.kernel_launches = launches;
    c->solved = true;
