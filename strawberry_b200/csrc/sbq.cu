@@ -18,6 +18,7 @@
 #include "../../include/sbq.h"
 #include "sbq_kernels.cuh"
 #include "sbq_grid.cuh"
+#include "sbq_grid_tma.cuh"
 
 using namespace sbq;
 
@@ -126,7 +127,9 @@ struct sbq_ctx {
    size_t warp_list_off = 0, grid_list_off = 0;
 
    // device
-   DevBuf d_in, d_out, d_lists, d_grid_scratch;
+   DevBuf d_in, d_out, d_lists, d_grid_scratch, d_col16;
+   bool col16_ready = false, grid_tma_ok = false;
+   int grid_max_iso = 1;
    DevParams dp{};
    double* d_tpm = nullptr;
    double* d_fpkm_sum = nullptr;
@@ -238,6 +241,8 @@ int plan(sbq_ctx* c) {
    c->grid_list.clear();
    c->classes.clear();
    c->warp_max_iso = 1;
+   c->grid_max_iso = 1;
+   c->grid_tma_ok = true;
    std::vector<int64_t> nnz_of(c->n_loci);
    LaunchClass* slot[5] = {};
    std::vector<LaunchClass> tmp;
@@ -260,6 +265,8 @@ int plan(sbq_ctx* c) {
          c->warp_max_iso = std::max(c->warp_max_iso, (int)T);
       } else if (tier == 3) {
          c->grid_list.push_back((int32_t)l);
+         c->grid_max_iso = std::max(c->grid_max_iso, (int)T);
+         if (!grid_tma_supports((int)T, (long long)R, c->prop.multiProcessorCount)) c->grid_tma_ok = false;
       } else {
          int cs = c->force_cluster ? c->force_cluster : cluster_size_for(nnz);
          int csi = cs == 1 ? 0 : cs == 2 ? 1 : cs == 4 ? 2 : cs == 8 ? 3 : 4;
@@ -412,7 +419,7 @@ void sbq_destroy(sbq_ctx* c) {
    c->h_lists.release();
    c->r_theta.release(); c->r_fpkm.release(); c->r_frac.release(); c->r_tpm.release();
    c->r_locus_fpkm.release(); c->r_keep.release(); c->r_iters.release(); c->r_status.release();
-   c->d_in.release(); c->d_out.release(); c->d_lists.release(); c->d_grid_scratch.release();
+   c->d_in.release(); c->d_out.release(); c->d_lists.release(); c->d_grid_scratch.release(); c->d_col16.release();
    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
    for (auto& e : c->ev_join) if (e) cudaEventDestroy(e);
@@ -545,9 +552,10 @@ int sbq_upload(sbq_ctx* c) {
    int rc = plan(c);
    if (rc) return rc;
 
-   const size_t sz_lro = align_up((c->n_loci + 1) * sizeof(int64_t)), sz_rp = align_up((c->n_row + 1) * sizeof(int64_t));
-   const size_t sz_col = align_up(c->nnz * sizeof(int32_t)), sz_al = align_up(c->nnz * sizeof(double));
-   const size_t sz_cnt = align_up(c->n_row * sizeof(int32_t)), sz_il = align_up(c->n_iso * sizeof(int32_t));
+   // +64 B of slack per array: the giant-locus kernel's 16-byte-granular bulk copies may read a few elements past the end
+   const size_t sz_lro = align_up((c->n_loci + 1) * sizeof(int64_t)), sz_rp = align_up((c->n_row + 1) * sizeof(int64_t) + 64);
+   const size_t sz_col = align_up(c->nnz * sizeof(int32_t) + 64), sz_al = align_up(c->nnz * sizeof(double) + 64);
+   const size_t sz_cnt = align_up(c->n_row * sizeof(int32_t) + 64), sz_il = align_up(c->n_iso * sizeof(int32_t));
    const size_t sz_csc = align_up(c->nnz * 4 + 16);
    const size_t in_bytes = 2 * sz_lro + sz_rp + sz_col + sz_al + 2 * sz_cnt + sz_il + sz_csc;
    const size_t sz_iso_d = align_up(c->n_iso * sizeof(double)), sz_iso_i = align_up(c->n_iso * sizeof(int32_t));
@@ -602,6 +610,7 @@ int sbq_upload(sbq_ctx* c) {
    c->stats.h2d_bytes = 2 * (c->n_loci + 1) * 8 + (c->n_row + 1) * 8 + c->nnz * 12 + c->n_row * 4 + c->n_iso * 4 + (int64_t)c->h_lists.n * 4;
    c->stats.n_loci = c->n_loci; c->stats.n_row = c->n_row; c->stats.n_iso = c->n_iso; c->stats.nnz = c->nnz;
    c->resident = true;
+   c->col16_ready = false;
    c->solved = c->downloaded = false;
    return SBQ_SUCCESS;
 }
@@ -632,8 +641,15 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
    if (!c->grid_list.empty()) {
       CU(cudaEventRecord(c->ev[6], st));
       int n_launch = 0;
-      int rc = grid_tier_launch(c->dp, c->d_lists_p + c->grid_list_off, (int)c->grid_list.size(), c->prop, &c->d_grid_scratch.p,
-                                &c->d_grid_scratch.cap, st, &n_launch);
+      int rc;
+      if (c->grid_tma_ok && !getenv("SBQ_GRID_NO_TMA")) {
+         rc = grid_tma_launch(c->dp, c->nnz, c->d_lists_p + c->grid_list_off, (int)c->grid_list.size(), c->grid_max_iso, c->prop,
+                              &c->d_grid_scratch.p, &c->d_grid_scratch.cap, &c->d_col16.p, &c->d_col16.cap, c->col16_ready, st, &n_launch);
+         if (rc == 0) c->col16_ready = true;
+      } else {
+         rc = grid_tier_launch(c->dp, c->d_lists_p + c->grid_list_off, (int)c->grid_list.size(), c->prop, &c->d_grid_scratch.p,
+                               &c->d_grid_scratch.cap, st, &n_launch);
+      }
       if (rc != 0) return fail(c, rc, "grid tier launch failed: %s", cudaGetErrorString(cudaGetLastError()));
       launches += n_launch;
       CU(cudaEventRecord(c->ev[7], st));
