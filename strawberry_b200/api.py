@@ -15,7 +15,7 @@ import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsbq.so")
+LIB_PATH = os.environ.get("SBQ_LIB_PATH", os.path.join(_HERE, "libsbq.so"))   # override: A/B-testing kernel variants
 
 SBQ_SUCCESS, SBQ_ERR_INVALID, SBQ_ERR_NO_DEVICE, SBQ_ERR_CUDA, SBQ_ERR_NOMEM, SBQ_ERR_STATE, SBQ_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 LOCUS_OK, LOCUS_ITER_CAP, LOCUS_ZERO_DENOM, LOCUS_NO_ROWS = 0, 1, 2, 3
