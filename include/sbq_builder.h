@@ -90,6 +90,10 @@ int  sbq_table_iso_segments(const sbq_table*, int32_t* iso_seg_ptr, int32_t* iso
 int  sbq_table_classes(const sbq_table*, int32_t* class_coord_ptr, int32_t* class_coord, int32_t* class_count,
                        float* class_mass, int32_t* class_nfrag);
 
+/* hit_class[n_hit]: class id of every input hit (the ExonBin whose _frags set it was offered to), -1 for hits
+ * that were dropped (ref_id -1) or are compatible with no isoform. */
+int  sbq_table_hit_classes(const sbq_table*, int32_t* hit_class);
+
 /* a11: feature list of one collapsed fragment from its mates' CIGARs (Contig::Contig(const PairedHit&)).
  * A mate with n_cig == 0 is absent. Returns the number of features written (0 = inconsistent
  * overlapping mates => ref_id -1), or a negative sbq_error (SBQ_ERR_INVALID if cap is too small). */

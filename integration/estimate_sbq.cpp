@@ -1,0 +1,187 @@
+// estimate_sbq.cpp - link-seam replacement for the reference's src/estimate.cpp.
+//
+// Compiled against the UNMODIFIED reference headers and linked with the reference's other objects in place of
+// estimate.o (integration/Makefile). It keeps exactly the symbols alignments.o imports from estimate.o
+// (LocusContext::assign_exon_bin / overlap_exons / set_theory_bin_weight / set_bin_weight_without_frag_dist /
+// estimate_abundances, LocusContext::_kMinFrac) and forwards the work to libsbq:
+//   class table + weights  -> sbq_build_locus   (host builder, include/sbq_builder.h)
+//   EM + FPKM/frac/filter  -> sbq_submit / sbq_run / sbq_results on the GPU (include/sbq.h)
+// Everything else (BAM/GTF I/O, clustering, TPM loop, GTF printing) is the reference's own code.
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "estimate.hpp"
+#include "sbq.h"
+#include "sbq_builder.h"
+
+using namespace std;
+
+const double LocusContext::_kMinFrac = kMinIsoformFrac;
+
+namespace {
+
+struct TableDeleter {
+   void operator()(sbq_table* t) const { sbq_table_free(t); }
+};
+// The constructor (header-inline, include/estimate.hpp:61-109) calls assign_exon_bin and then one of the two
+// weight setters on the same thread: the table built by the first call is handed to the second through this slot.
+thread_local unique_ptr<sbq_table, TableDeleter> tl_table;
+
+mutex g_ctx_mu;
+sbq_ctx* g_ctx = nullptr;
+
+sbq_ctx* context() {   // caller holds g_ctx_mu
+   if (!g_ctx) {
+      sbq_config cfg;
+      sbq_config_default(&cfg);
+      cfg.min_iso_frac = kMinIsoformFrac;                 // -m / forced 0 with -r (src/Strawberry.cpp:158-162)
+      cfg.effective_len_norm = effective_len_norm ? 1 : 0;
+      const int rc = sbq_create(&cfg, &g_ctx);
+      if (rc != SBQ_SUCCESS) {
+         fprintf(stderr, "libsbq: %s\n", sbq_error_string(rc));
+         exit(1);
+      }
+   }
+   return g_ctx;
+}
+
+void flatten(const vector<GenomicFeature>& feats, vector<uint32_t>& off, vector<uint32_t>& len, vector<uint8_t>& code) {
+   for (auto const& f : feats) {
+      off.push_back(f._genomic_offset);
+      len.push_back(f._match_op._len);
+      code.push_back((uint8_t)f._match_op._code);
+   }
+}
+
+}  // namespace
+
+set<pair<uint, uint>> LocusContext::overlap_exons(const vector<GenomicFeature>& exons, const Contig& read) const {
+   // segments that any aligned block of the read touches (closed intervals); still needed by the header-inline
+   // get_frag_info() for the -f fragment-context output
+   set<pair<uint, uint>> coords;
+   for (auto const& seg : exons) {
+      if (seg._match_op._code != Match_t::S_MATCH) continue;
+      for (auto const& f : read._genomic_feats)
+         if (f._match_op._code == Match_t::S_MATCH && f.left() <= seg.right() && seg.left() <= f.right()) {
+            coords.insert(make_pair(seg.left(), seg.right()));
+            break;
+         }
+   }
+   return coords;
+}
+
+void LocusContext::assign_exon_bin(const vector<Contig>& hits, const vector<GenomicFeature>& exon_segs) {
+   // flatten the locus and let the libsbq host builder make the class table and the weights
+   vector<int32_t> iso_ptr(1, 0), hit_ptr(1, 0), ref_ids;
+   vector<uint32_t> ioff, ilen, hoff, hlen;
+   vector<uint8_t> icode, hcode;
+   vector<double> mass;
+   for (auto const& iso : _transcripts) {
+      flatten(iso._contig._genomic_feats, ioff, ilen, icode);
+      iso_ptr.push_back((int32_t)ioff.size());
+   }
+   for (auto const& h : hits) {
+      flatten(h._genomic_feats, hoff, hlen, hcode);
+      hit_ptr.push_back((int32_t)hoff.size());
+      mass.push_back((double)h.mass());
+      ref_ids.push_back(h.ref_id());
+   }
+   const InsertSize& ins = *_sample._insert_size_dist;
+   sbq_insert_model model{ins._use_emp ? 1 : 0, ins._use_emp ? ins._start_offset : 0, ins._use_emp ? ins._end_offset : 0,
+                          ins._use_emp ? ins._emp_dist.data() : nullptr, ins._use_emp ? ins._total_reads : 0, ins._mean, ins._sd};
+   sbq_locus_input in{(int32_t)_transcripts.size(), iso_ptr.data(), ioff.data(), ilen.data(), icode.data(),
+                      (int32_t)hits.size(), hit_ptr.data(), hoff.data(), hlen.data(), hcode.data(), mass.data(), ref_ids.data(),
+                      _read_len, long_read_sample ? 1 : 0};
+   sbq_table* tb = nullptr;
+   const int rc = sbq_build_locus(&in, &model, &tb);
+   if (rc != SBQ_SUCCESS) {
+      fprintf(stderr, "libsbq: sbq_build_locus: %s\n", sbq_error_string(rc));
+      exit(1);
+   }
+   tl_table.reset(tb);
+
+   sbq_table_dims d;
+   sbq_table_get_dims(tb, &d);
+   assert((size_t)d.n_seg == exon_segs.size());
+   vector<int32_t> cptr(d.n_class + 1), coord(max<int64_t>(1, d.n_coord)), hclass(max<size_t>(1, hits.size()));
+   sbq_table_classes(tb, cptr.data(), coord.data(), nullptr, nullptr, nullptr);
+   sbq_table_hit_classes(tb, hclass.data());
+   exon_bins.clear();
+   for (int c = 0; c < d.n_class; ++c) {
+      set<pair<uint, uint>> coords;
+      for (int k = cptr[c]; k < cptr[c + 1]; ++k) coords.insert(make_pair(exon_segs[coord[k]].left(), exon_segs[coord[k]].right()));
+      ExonBin eb(coords);
+      eb.id() = c;
+      exon_bins.push_back(eb);
+   }
+   for (size_t h = 0; h < hits.size(); ++h)
+      if (hclass[h] >= 0) exon_bins[hclass[h]].add_frag(hits[h]);   // keeps read_count() / get_frag_info() working
+   sbq_locus L;
+   sbq_table_locus(tb, &L);
+   for (int c = 0; c < L.n_row; ++c)
+      for (int64_t k = L.row_ptr[c]; k < L.row_ptr[c + 1]; ++k) iso_2_bins_map[L.col[k]].insert(c);
+}
+
+static void weights_from_table(vector<ExonBin>& bins) {
+   sbq_locus L;
+   sbq_table_locus(tl_table.get(), &L);
+   for (int c = 0; c < L.n_row; ++c)
+      for (int64_t k = L.row_ptr[c]; k < L.row_ptr[c + 1]; ++k) bins[c]._bin_weight_map[L.col[k]] = L.alpha[k];
+   tl_table.reset();
+}
+
+void LocusContext::set_theory_bin_weight() { weights_from_table(exon_bins); }
+void LocusContext::set_bin_weight_without_frag_dist() { weights_from_table(exon_bins); }
+
+bool LocusContext::estimate_abundances() {
+   const size_t nrow = exon_bins.size(), niso = _transcripts.size();
+   vector<int64_t> row_ptr(1, 0);
+   vector<int32_t> col, count, iso_len;
+   vector<double> alpha;
+   for (auto const& bin : exon_bins) {
+      count.push_back((int)bin.read_count());
+      for (auto const& w : bin._bin_weight_map) { col.push_back(w.first); alpha.push_back(w.second); }
+      row_ptr.push_back((int64_t)col.size());
+   }
+   for (auto const& t : _transcripts) iso_len.push_back(t._length);
+   sbq_locus L{(int32_t)niso, (int32_t)nrow, row_ptr.data(), col.data(), alpha.data(), count.data(), iso_len.data()};
+   vector<double> theta(niso), fpkm(niso), frac(niso);
+   vector<int32_t> keep(niso);
+   int32_t iters = 0, status = 0;
+   {
+      lock_guard<mutex> lk(g_ctx_mu);
+      sbq_ctx* c = context();
+      int rc = sbq_clear(c);
+      if (!rc) rc = sbq_submit(c, &L, 1);
+      if (!rc) rc = sbq_run(c, _sample.total_mapped_reads());
+      if (!rc) rc = sbq_results(c, theta.data(), fpkm.data(), frac.data(), nullptr, keep.data(), &iters, &status);
+      if (rc) {
+         fprintf(stderr, "libsbq: %s (%s)\n", sbq_error_string(rc), sbq_last_error(c));
+         exit(1);
+      }
+   }
+   const bool success = status != SBQ_LOCUS_NO_ROWS;
+   if (!success) return false;
+   for (size_t i = 0; i < niso; ++i) fprintf(_p_log_file, "isoform %d has %f raw read count.\n", (int)i + 1, theta[i]);
+   for (size_t i = 0; i < niso; ++i) {
+      if (keep[i] < 0) {                       // effective_len_norm "NA" case
+         _transcripts[i]._FPKM_s = "NA";
+         _transcripts[i]._frac_s = "NA";
+         continue;
+      }
+      _transcripts[i]._FPKM = fpkm[i];
+      _transcripts[i]._FPKM_s = to_string(fpkm[i]);
+      _transcripts[i]._frac = frac[i];
+      _transcripts[i]._frac_s = to_string(frac[i]);
+   }
+   if (filter_by_expression) {
+      size_t i = 0;
+      for (auto it = _transcripts.begin(); it != _transcripts.end(); ++i) {
+         if (keep[i] == 0) it = _transcripts.erase(it); else ++it;
+      }
+   }
+   return true;
+}

@@ -14,7 +14,7 @@ MATCH, INTRON, GAP = 0, 1, 2
 CIG_M, CIG_I, CIG_D, CIG_N, CIG_S = 0, 1, 2, 3, 4
 
 BUILDER_SYMBOLS = ["sbq_build_locus", "sbq_table_free", "sbq_table_locus", "sbq_table_get_dims", "sbq_table_segments",
-                   "sbq_table_iso_segments", "sbq_table_classes", "sbq_pair_features", "sbq_effective_len", "sbq_insert_pdf"]
+                   "sbq_table_iso_segments", "sbq_table_classes", "sbq_table_hit_classes", "sbq_pair_features", "sbq_effective_len", "sbq_insert_pdf"]
 
 
 class InsertModel(ctypes.Structure):
@@ -45,6 +45,7 @@ def _lib():
         L.sbq_table_segments.argtypes = [ctypes.c_void_p] * 3
         L.sbq_table_iso_segments.argtypes = [ctypes.c_void_p] * 3
         L.sbq_table_classes.argtypes = [ctypes.c_void_p] * 6
+        L.sbq_table_hit_classes.argtypes = [ctypes.c_void_p] * 2
         L.sbq_pair_features.argtypes = [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                         ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]
@@ -142,6 +143,8 @@ def build_locus(transcripts, hits, *, read_len, model=None, long_read=False, ref
         cp, cc = np.zeros(d.n_class + 1, np.int32), np.zeros(max(1, d.n_coord), np.int32)
         cnt, cm, nf = np.zeros(max(1, d.n_class), np.int32), np.zeros(max(1, d.n_class), np.float32), np.zeros(max(1, d.n_class), np.int32)
         L.sbq_table_classes(h, cp.ctypes.data, cc.ctypes.data, cnt.ctypes.data, cm.ctypes.data, nf.ctypes.data)
+        hcl = np.full(max(1, len(hits)), -1, np.int32)
+        L.sbq_table_hit_classes(h, hcl.ctypes.data)
         loc = api.Locus()
         L.sbq_table_locus(h, ctypes.byref(loc))
 
@@ -157,7 +160,7 @@ def build_locus(transcripts, hits, *, read_len, model=None, long_read=False, ref
             classes=[dict(coords=[int(x) for x in cc[cp[c]:cp[c + 1]]], count=int(cnt[c]), mass=float(cm[c]), nfrag=int(nf[c]))
                      for c in range(d.n_class)],
             row_ptr=row_ptr, col=view(loc.col, d.nnz, np.int32), alpha=view(loc.alpha, d.nnz, np.float64),
-            count=cnt[:d.n_class].copy(), n_dropped=d.n_dropped_hits, n_iso=d.n_iso)
+            count=cnt[:d.n_class].copy(), n_dropped=d.n_dropped_hits, n_iso=d.n_iso, hit_class=hcl[:len(hits)].copy())
     finally:
         L.sbq_table_free(h)
     return out

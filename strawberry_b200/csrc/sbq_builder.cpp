@@ -184,6 +184,7 @@ struct sbq_table {
    std::vector<int32_t> col;
    std::vector<double> alpha;
    std::vector<int32_t> iso_len;
+   std::vector<int32_t> hit_class;   // class of every input hit, -1 = dropped / compatible with nothing
    int32_t n_dropped = 0;
 };
 
@@ -339,6 +340,7 @@ int sbq_build_locus(const sbq_locus_input* in, const sbq_insert_model* model, sb
    std::vector<std::map<FragKey, float, FragLess>> class_frags;
    std::vector<std::vector<int32_t>> iso_classes(T);   // kept sorted & unique (std::set<int> in the reference)
    std::vector<int32_t> coords;
+   tb->hit_class.assign(in->n_hit > 0 ? in->n_hit : 0, -1);
    for (int h = 0; h < in->n_hit; ++h) {
       const FeatList H = hit_list(h);
       if (H.n == 0) { ++tb->n_dropped; continue; }   // Contig with ref_id == -1 (include/estimate.hpp:71-79)
@@ -358,6 +360,7 @@ int sbq_build_locus(const sbq_locus_input* in, const sbq_insert_model* model, sb
          if (coords.empty()) continue;
          auto ins = class_of.emplace(coords, (int32_t)class_coords.size());
          const int32_t cid = ins.first->second;
+         tb->hit_class[h] = cid;
          if (ins.second) { class_coords.push_back(coords); class_frags.emplace_back(); }
          const int32_t ref_id = in->hit_ref_id ? in->hit_ref_id[h] : 0;
          class_frags[cid].emplace(FragKey{ref_id, H}, (float)in->hit_mass[h]);   // set::insert: first one wins
@@ -467,6 +470,12 @@ int sbq_table_iso_segments(const sbq_table* t, int32_t* ptr, int32_t* seg) {
    if (!t) return SBQ_ERR_INVALID;
    if (ptr) memcpy(ptr, t->iso_seg_ptr.data(), t->iso_seg_ptr.size() * sizeof(int32_t));
    if (seg) memcpy(seg, t->iso_seg.data(), t->iso_seg.size() * sizeof(int32_t));
+   return SBQ_SUCCESS;
+}
+
+int sbq_table_hit_classes(const sbq_table* t, int32_t* hit_class) {
+   if (!t || !hit_class) return SBQ_ERR_INVALID;
+   memcpy(hit_class, t->hit_class.data(), t->hit_class.size() * sizeof(int32_t));
    return SBQ_SUCCESS;
 }
 
