@@ -57,6 +57,11 @@ typedef struct {
    int32_t bias_mode;          /* 0 = reference behaviour. 1 = bias-corrected EM, OUR definition    */
                                /*     (DESIGN.md "Bias mode"); the reference has none (bias.cpp     */
                                /*     is commented out) - parity unpinned                           */
+   /* bias mode only; defaults are the constants the reference declares but never reads              */
+   int32_t max_out_it;         /* EmSolver::_max_out_it_num          include/estimate.hpp:239   100 */
+   int32_t max_theta_it;       /* EmSolver::_max_theta_it_num        include/estimate.hpp:238  5000 */
+   int32_t max_bias_it;        /* EmSolver::_max_bias_it_num         include/estimate.hpp:237    10 */
+   double  bias_tol;           /* EmSolver::_bias_change_limit       include/estimate.hpp:241  1e-2 */
 } sbq_config;
 
 /* One locus as the host class-table builder emits it: what LocusContext::estimate_abundances
@@ -174,6 +179,12 @@ int  sbq_get_launch_stats(const sbq_ctx*, sbq_launch_stat* out, int cap);
 /* Single-locus convenience backing a drop-in EmSolver (EmSolver::init + run, src/estimate.cpp:366-488):
  * theta receives n_iso doubles; returns the sbq_locus_status (>= 0) or a negative sbq_error. */
 int  sbq_em_solve(sbq_ctx*, const sbq_locus* locus, double* theta, int32_t* iters);
+
+/* Bias mode (bias_mode = 1, OUR definition - DESIGN.md section 7; no reference behaviour exists). Per-row
+ * covariates x[n_row][n_cov] (row-major, rows in submit order, n_cov <= 6) must be set after the last sbq_submit*
+ * and before sbq_upload / sbq_run; sbq_bias_results returns beta[n_loci][n_cov] and the outer rounds per locus. */
+int  sbq_set_covariates(sbq_ctx*, const double* x, int64_t n_row, int32_t n_cov);
+int  sbq_bias_results(sbq_ctx*, double* beta, int32_t* outer_iters);
 
 /* Planner knobs, mainly for tests: force a tier (0 = auto, 1 = warp, 2 = CTA/cluster, 3 = grid) and
  * the cluster size of the CTA tier (0 = auto, else 1, 2, 4, 8, 16). */

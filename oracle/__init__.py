@@ -138,6 +138,27 @@ def quantify_batch(batch, total_mapped_reads, min_iso_frac=0.0, effective_len_no
     return dict(theta=theta, fpkm=fpkm, frac=frac, tpm=tpm, keep=keep, iters=iters, status=status, seconds=secs)
 
 
+class _BiasParams(ctypes.Structure):
+    _fields_ = [("max_out_it", ctypes.c_int), ("max_theta_it", ctypes.c_int), ("max_bias_it", ctypes.c_int),
+                ("theta_tol", ctypes.c_double), ("bias_tol", ctypes.c_double), ("row_eps", ctypes.c_double)]
+
+
+def em_bias_csr(T, row_ptr, col, alpha, count, x, max_out_it=100, max_theta_it=5000, max_bias_it=10, theta_tol=1e-2,
+                bias_tol=1e-2, row_eps=1e-5):
+    """Bias mode restatement (OUR definition; parity unpinned vs the reference). -> (status, theta, beta, iters, outer)"""
+    row_ptr, col = _c(row_ptr, np.int64), _c(col, np.int32)
+    alpha, count, x = _c(alpha, np.float64), _c(count, np.int32), _c(x, np.float64)
+    K = x.shape[1] if x.ndim == 2 else 0
+    theta, beta = np.zeros(T), np.zeros(max(K, 1))
+    iters, outer = ctypes.c_int32(0), ctypes.c_int32(0)
+    p = _BiasParams(max_out_it, max_theta_it, max_bias_it, theta_tol, bias_tol, row_eps)
+    L = oracle_lib()
+    L.orc_em_bias_csr.restype = ctypes.c_int
+    st = L.orc_em_bias_csr(T, len(count), _p(row_ptr), _p(col), _p(alpha), _p(count), _p(x) if x.size else None, K, ctypes.byref(p),
+                           _p(theta), _p(beta), ctypes.byref(iters), ctypes.byref(outer))
+    return st, theta, beta[:K], iters.value, outer.value
+
+
 # ---------------------------------------------------------------- compiled reference (_ref/libsbref.so)
 def ref_em(count, alpha):
     """EmSolver::init + run of the unmodified reference. -> (rc, theta); rc bit0 init ok, bit1 run ok."""

@@ -237,3 +237,127 @@ double orc_quantify_batch(int64_t n_loci, const int64_t* loc_row_off, const int6
    clock_gettime(CLOCK_MONOTONIC, &t1);
    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Bias mode: OUR definition (see sbq_oracle.h). No reference behaviour exists - parity unpinned. */
+static int solve_spd(int K, double* H, double* g) {
+   /* Gaussian elimination with partial pivoting on the K x K system H d = g (H row-major); d returned in g */
+   for (int c = 0; c < K; ++c) {
+      int piv = c;
+      for (int r = c + 1; r < K; ++r)
+         if (fabs(H[r * K + c]) > fabs(H[piv * K + c])) piv = r;
+      if (H[piv * K + c] == 0.0) return 0;
+      if (piv != c) {
+         for (int k = 0; k < K; ++k) { double t = H[c * K + k]; H[c * K + k] = H[piv * K + k]; H[piv * K + k] = t; }
+         double t = g[c]; g[c] = g[piv]; g[piv] = t;
+      }
+      for (int r = c + 1; r < K; ++r) {
+         const double f = H[r * K + c] / H[c * K + c];
+         for (int k = c; k < K; ++k) H[r * K + k] -= f * H[c * K + k];
+         g[r] -= f * g[c];
+      }
+   }
+   for (int c = K - 1; c >= 0; --c) {
+      double v = g[c];
+      for (int k = c + 1; k < K; ++k) v -= H[c * K + k] * g[k];
+      g[c] = v / H[c * K + c];
+   }
+   return 1;
+}
+
+int orc_em_bias_csr(int T, int R, const int64_t* row_ptr, const int32_t* col, const double* alpha, const int32_t* count,
+                    const double* x, int K, const orc_bias_params* p, double* theta, double* beta, int32_t* iters,
+                    int32_t* outer_iters) {
+   double total = 0.0;
+   for (int i = 0; i < R; ++i) total += count[i];
+   for (int j = 0; j < T; ++j) theta[j] = total / T;
+   for (int k = 0; k < K; ++k) beta[k] = 0.0;
+   *iters = 0;
+   *outer_iters = 0;
+   char* keep = (char*)calloc((size_t)(R > 0 ? R : 1), 1);
+   int Rk = 0;
+   for (int i = 0; i < R; ++i) {
+      for (int64_t k = row_ptr[i]; k < row_ptr[i + 1]; ++k)
+         if (alpha[k] > p->row_eps) keep[i] = 1;
+      Rk += keep[i];
+   }
+   if (Rk == 0) { free(keep); return ORC_NO_ROWS; }
+   double* w = (double*)malloc(sizeof(double) * (size_t)R);
+   double* d = (double*)malloc(sizeof(double) * (size_t)R);
+   double* s = (double*)malloc(sizeof(double) * (size_t)T);
+   double* th = (double*)malloc(sizeof(double) * (size_t)T);
+   double* next = (double*)malloc(sizeof(double) * (size_t)T);
+   double* cur = (double*)malloc(sizeof(double) * (size_t)T);
+   double H[64], g[8], bprev[8];
+   for (int i = 0; i < R; ++i) w[i] = 1.0;
+   memcpy(cur, theta, sizeof(double) * (size_t)T);
+   int status = ORC_ITER_CAP;
+   for (int out = 0; out < p->max_out_it; ++out) {
+      *outer_iters = out + 1;
+      for (int j = 0; j < T; ++j) s[j] = 0.0;
+      for (int i = 0; i < R; ++i)
+         if (keep[i])
+            for (int64_t k = row_ptr[i]; k < row_ptr[i + 1]; ++k) s[col[k]] += alpha[k] * w[i];
+      /* theta-EM with the current bias */
+      int conv = 0;
+      for (int it = 0; it < p->max_theta_it; ++it) {
+         *iters += 1;
+         for (int j = 0; j < T; ++j) { th[j] = s[j] != 0 ? cur[j] / s[j] : 0.0; next[j] = 0.0; }
+         for (int i = 0; i < R; ++i) {
+            if (!keep[i]) continue;
+            double dd = 0.0;
+            for (int64_t k = row_ptr[i]; k < row_ptr[i + 1]; ++k) dd += alpha[k] * th[col[k]];
+            if (dd == 0) { status = ORC_ZERO_DENOM; goto done; }
+            const double r = (double)count[i] / dd;
+            for (int64_t k = row_ptr[i]; k < row_ptr[i + 1]; ++k) next[col[k]] += alpha[k] * th[col[k]] * r;
+         }
+         double d2 = 0.0;
+         for (int j = 0; j < T; ++j) d2 += (next[j] - cur[j]) * (next[j] - cur[j]);
+         memcpy(cur, next, sizeof(double) * (size_t)T);
+         if (sqrt(d2) < p->theta_tol) { conv = 1; break; }
+      }
+      (void)conv;
+      if (K == 0) { status = ORC_OK; break; }
+      /* bias update: Newton steps of the Poisson log-linear fit with d_i fixed */
+      for (int j = 0; j < T; ++j) th[j] = s[j] != 0 ? cur[j] / s[j] : 0.0;
+      for (int i = 0; i < R; ++i) {
+         d[i] = 0.0;
+         if (keep[i])
+            for (int64_t k = row_ptr[i]; k < row_ptr[i + 1]; ++k) d[i] += alpha[k] * th[col[k]];
+      }
+      memcpy(bprev, beta, sizeof(double) * (size_t)K);
+      for (int nb = 0; nb < p->max_bias_it; ++nb) {
+         for (int a = 0; a < K * K; ++a) H[a] = 0.0;
+         for (int a = 0; a < K; ++a) g[a] = 0.0;
+         double tr = 0.0;
+         for (int i = 0; i < R; ++i) {
+            if (!keep[i]) continue;
+            const double mu = w[i] * d[i];
+            const double* xi = x + (size_t)i * K;
+            for (int a = 0; a < K; ++a) {
+               g[a] += ((double)count[i] - mu) * xi[a];
+               for (int b = 0; b < K; ++b) H[a * K + b] += mu * xi[a] * xi[b];
+            }
+         }
+         for (int a = 0; a < K; ++a) tr += H[a * K + a];
+         for (int a = 0; a < K; ++a) H[a * K + a] += 1e-9 * tr + 1e-12;   /* ridge */
+         if (!solve_spd(K, H, g)) break;
+         double n2 = 0.0;
+         for (int a = 0; a < K; ++a) { beta[a] += g[a]; n2 += g[a] * g[a]; }
+         for (int i = 0; i < R; ++i) {
+            double e = 0.0;
+            for (int a = 0; a < K; ++a) e += beta[a] * x[(size_t)i * K + a];
+            e = e > 30.0 ? 30.0 : (e < -30.0 ? -30.0 : e);
+            w[i] = exp(e);
+         }
+         if (sqrt(n2) < p->bias_tol) break;
+      }
+      double m2 = 0.0;
+      for (int a = 0; a < K; ++a) m2 += (beta[a] - bprev[a]) * (beta[a] - bprev[a]);
+      if (sqrt(m2) < p->bias_tol) { status = ORC_OK; break; }
+   }
+   memcpy(theta, cur, sizeof(double) * (size_t)T);
+done:
+   free(keep); free(w); free(d); free(s); free(th); free(next); free(cur);
+   return status;
+}

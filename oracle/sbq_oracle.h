@@ -54,6 +54,25 @@ double orc_quantify_batch(int64_t n_loci, const int64_t* loc_row_off, const int6
                           double* theta, double* fpkm, double* frac, double* tpm, int32_t* keep,
                           int32_t* iters, int32_t* status);
 
+/* Bias mode (bias_mode = 1) - OUR definition; the reference has none (src/bias.cpp is commented
+ * out), so this restatement is the only oracle of that mode: PARITY UNPINNED against the reference.
+ *   row weight w_i = exp(clamp(beta . x_i, +-30)), biased model F_ij = alpha_ij w_i, s_j = sum_kept alpha_ij w_i
+ *   outer loop (<= max_out_it): theta-EM to ||theta' - theta|| < theta_tol (<= max_theta_it, theta advanced),
+ *   then <= max_bias_it Newton steps of the Poisson log-linear fit n_i ~ w_i * d_i (d_i = sum_j alpha_ij theta_j / s_j
+ *   held fixed), stop when ||delta beta|| < bias_tol; outer stop when beta moved less than bias_tol.
+ * x is row-major R x n_cov. Returns the locus status; iters = total theta-EM iterations. */
+typedef struct {
+   int max_out_it;      /* EmSolver::_max_out_it_num   = 100   include/estimate.hpp:239 (declared, never read) */
+   int max_theta_it;    /* EmSolver::_max_theta_it_num = 5000  include/estimate.hpp:238 */
+   int max_bias_it;     /* EmSolver::_max_bias_it_num  = 10    include/estimate.hpp:237 */
+   double theta_tol;    /* 1e-2 */
+   double bias_tol;     /* EmSolver::_bias_change_limit = 1e-2 include/estimate.hpp:241 */
+   double row_eps;      /* 1e-5 */
+} orc_bias_params;
+int orc_em_bias_csr(int T, int R, const int64_t* row_ptr, const int32_t* col, const double* alpha, const int32_t* count,
+                    const double* x, int n_cov, const orc_bias_params* p, double* theta, double* beta, int32_t* iters,
+                    int32_t* outer_iters);
+
 #ifdef __cplusplus
 }
 #endif

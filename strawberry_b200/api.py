@@ -26,6 +26,7 @@ ABI_SYMBOLS = [
     "sbq_submit", "sbq_submit_flat", "sbq_clear", "sbq_validate", "sbq_host_alloc", "sbq_host_free",
     "sbq_upload", "sbq_solve", "sbq_download", "sbq_run", "sbq_fpkm_sum", "sbq_fpkm_sum_to_device",
     "sbq_finalize_tpm", "sbq_results", "sbq_get_stats", "sbq_get_launch_stats", "sbq_em_solve", "sbq_set_plan",
+    "sbq_set_covariates", "sbq_bias_results",
 ]
 
 
@@ -39,7 +40,8 @@ class Config(ctypes.Structure):
     _fields_ = [("device", ctypes.c_int32), ("max_iter", ctypes.c_int32), ("theta_tol", ctypes.c_double),
                 ("row_eps", ctypes.c_double), ("min_iso_frac", ctypes.c_double),
                 ("effective_len_norm", ctypes.c_int32), ("insert_mean", ctypes.c_double),
-                ("bias_mode", ctypes.c_int32)]
+                ("bias_mode", ctypes.c_int32), ("max_out_it", ctypes.c_int32), ("max_theta_it", ctypes.c_int32),
+                ("max_bias_it", ctypes.c_int32), ("bias_tol", ctypes.c_double)]
 
 
 class Locus(ctypes.Structure):
@@ -98,6 +100,8 @@ def lib():
         L.sbq_get_launch_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(LaunchStat), ctypes.c_int]
         L.sbq_em_solve.argtypes = [ctypes.c_void_p, ctypes.POINTER(Locus), ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32)]
         L.sbq_set_plan.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.sbq_set_covariates.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32]
+        L.sbq_bias_results.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         _lib = L
     return _lib
 
@@ -192,6 +196,19 @@ class Quantifier:
             arr.append(Locus(int(n_iso), len(n), rp.ctypes.data, c.ctypes.data, a.ctypes.data, n.ctypes.data, il.ctypes.data))
         buf = (Locus * len(arr))(*arr)
         self._chk(self._L.sbq_submit(self._h, buf, len(arr)))
+
+    def set_covariates(self, x):
+        """bias mode: per-row covariates, shape (n_row, n_cov), rows in submit order"""
+        x = _c(x, np.float64)
+        self._n_cov = x.shape[1] if x.ndim == 2 else 0
+        self._chk(self._L.sbq_set_covariates(self._h, _ptr(x) if x.size else None, x.shape[0], self._n_cov))
+
+    def bias_results(self):
+        nl = self.stats()["n_loci"]
+        beta = np.zeros((nl, max(self._n_cov, 1)))
+        outer = np.zeros(nl, np.int32)
+        self._chk(self._L.sbq_bias_results(self._h, _ptr(beta), _ptr(outer)))
+        return beta[:, :self._n_cov], outer
 
     def validate(self):
         self._chk(self._L.sbq_validate(self._h))

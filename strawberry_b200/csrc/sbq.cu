@@ -19,6 +19,7 @@
 #include "sbq_kernels.cuh"
 #include "sbq_grid.cuh"
 #include "sbq_grid_tma.cuh"
+#include "sbq_bias.cuh"
 
 using namespace sbq;
 
@@ -118,6 +119,16 @@ struct sbq_ctx {
    const double* b_alpha = nullptr;
    int64_t n_loci = 0, n_row = 0, n_iso = 0, nnz = 0;
 
+   // bias mode
+   PinnedVec<double> h_cov;
+   int n_cov = 0;
+   bool have_cov = false;
+   DevBuf d_bias;
+   BiasParams bpar{};
+   PinnedVec<double> r_beta;
+   PinnedVec<int32_t> r_outer;
+   int max_iso_all = 1;
+
    // plan
    int force_tier = 0, force_cluster = 0;
    std::vector<int32_t> warp_list, grid_list;
@@ -204,6 +215,8 @@ void reset_batch(sbq_ctx* c) {
    c->h_loc_row_off.clear(); c->h_loc_iso_off.clear(); c->h_row_ptr.clear();
    c->h_col.clear(); c->h_count.clear(); c->h_iso_len.clear(); c->h_alpha.clear();
    c->n_loci = c->n_row = c->n_iso = c->nnz = 0;
+   c->have_cov = false;
+   c->h_cov.clear();
    c->resident = c->solved = c->downloaded = false;
 }
 
@@ -241,6 +254,7 @@ int plan(sbq_ctx* c) {
    c->grid_list.clear();
    c->classes.clear();
    c->warp_max_iso = 1;
+   c->max_iso_all = 1;
    c->grid_max_iso = 1;
    c->grid_tma_ok = true;
    std::vector<int64_t> nnz_of(c->n_loci);
@@ -252,6 +266,7 @@ int plan(sbq_ctx* c) {
       const int64_t R = lro[l + 1] - lro[l], T = lio[l + 1] - lio[l];
       const int64_t nnz = rp[lro[l + 1]] - rp[lro[l]];
       nnz_of[l] = nnz;
+      c->max_iso_all = std::max(c->max_iso_all, (int)T);
       if (T > SBQ_MAX_ISO) return fail(c, SBQ_ERR_UNSUPPORTED, "locus %lld has %lld isoforms (> SBQ_MAX_ISO)", (long long)l, (long long)T);
       int tier;
       if (c->force_tier) tier = c->force_tier;
@@ -373,12 +388,17 @@ void sbq_config_default(sbq_config* cfg) {
    cfg->effective_len_norm = 0;
    cfg->insert_mean = 0.0;
    cfg->bias_mode = 0;
+   cfg->max_out_it = 100;
+   cfg->max_theta_it = 5000;
+   cfg->max_bias_it = 10;
+   cfg->bias_tol = 1e-2;
 }
 
 int sbq_create(const sbq_config* cfg, sbq_ctx** out) {
    if (!cfg || !out) return SBQ_ERR_INVALID;
    *out = nullptr;
    if (cfg->max_iter < 1 || !(cfg->theta_tol >= 0) || cfg->bias_mode < 0 || cfg->bias_mode > 1) return SBQ_ERR_INVALID;
+   if (cfg->bias_mode == 1 && (cfg->max_out_it < 1 || cfg->max_theta_it < 1 || cfg->max_bias_it < 1 || !(cfg->bias_tol >= 0))) return SBQ_ERR_INVALID;
    int ndev = 0;
    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
       cudaGetLastError();
@@ -419,7 +439,8 @@ void sbq_destroy(sbq_ctx* c) {
    c->h_lists.release();
    c->r_theta.release(); c->r_fpkm.release(); c->r_frac.release(); c->r_tpm.release();
    c->r_locus_fpkm.release(); c->r_keep.release(); c->r_iters.release(); c->r_status.release();
-   c->d_in.release(); c->d_out.release(); c->d_lists.release(); c->d_grid_scratch.release(); c->d_col16.release();
+   c->d_in.release(); c->d_out.release(); c->d_lists.release(); c->d_grid_scratch.release(); c->d_col16.release(); c->d_bias.release();
+   c->h_cov.release(); c->r_beta.release(); c->r_outer.release();
    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
    for (auto& e : c->ev_join) if (e) cudaEventDestroy(e);
@@ -609,6 +630,22 @@ int sbq_upload(sbq_ctx* c) {
    c->stats.upload_ms = ms;
    c->stats.h2d_bytes = 2 * (c->n_loci + 1) * 8 + (c->n_row + 1) * 8 + c->nnz * 12 + c->n_row * 4 + c->n_iso * 4 + (int64_t)c->h_lists.n * 4;
    c->stats.n_loci = c->n_loci; c->stats.n_row = c->n_row; c->stats.n_iso = c->n_iso; c->stats.nnz = c->nnz;
+   if (c->cfg.bias_mode == 1) {
+      if (!c->have_cov) return fail(c, SBQ_ERR_STATE, "bias_mode = 1 needs sbq_set_covariates() after the last submit");
+      const size_t K = (size_t)c->n_cov;
+      const size_t bx = align_up(c->n_row * K * 8 + 8), bw = align_up(c->n_row * 8 + 8), bb = align_up(c->n_loci * K * 8 + 8), bo = align_up(c->n_loci * 4 + 8);
+      if (!c->d_bias.reserve(bx + 2 * bw + bb + bo)) return fail(c, SBQ_ERR_NOMEM, "device allocation failed (bias scratch)");
+      char* q = (char*)c->d_bias.p;
+      c->bpar.x = (const double*)q; q += bx;
+      c->bpar.w = (double*)q; q += bw;
+      c->bpar.d = (double*)q; q += bw;
+      c->bpar.beta = (double*)q; q += bb;
+      c->bpar.outer = (int32_t*)q;
+      c->bpar.n_cov = c->n_cov;
+      if (K) CU(cudaMemcpyAsync((void*)c->bpar.x, c->h_cov.p, c->n_row * K * 8, cudaMemcpyHostToDevice, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      c->stats.h2d_bytes += (int64_t)(c->n_row * K * 8);
+   }
    c->resident = true;
    c->col16_ready = false;
    c->solved = c->downloaded = false;
@@ -620,7 +657,7 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
    std::lock_guard<std::mutex> lk(c->mu);
    CU(cudaSetDevice(c->device));
    if (!c->resident) return fail(c, SBQ_ERR_STATE, "sbq_solve before sbq_upload");
-   if (c->cfg.bias_mode != 0) return fail(c, SBQ_ERR_UNSUPPORTED, "bias_mode=1 is not implemented yet in this build");
+
    DevParams& dp = c->dp;
    dp.max_iter = c->cfg.max_iter;
    dp.tol = c->cfg.theta_tol;
@@ -632,6 +669,36 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
 
    cudaStream_t st = c->stream;
    int64_t launches = 0;
+   if (c->cfg.bias_mode == 1) {
+      // bias-corrected EM: one fused kernel (theta-EM + bias-weight update + both convergence tests), one CTA per locus
+      const size_t smem = bias_smem_bytes(c->max_iso_all);
+      if (smem > SMEM_CAP) return fail(c, SBQ_ERR_UNSUPPORTED, "bias mode supports up to %d isoforms per locus", (int)(SMEM_CAP / (8 * (4 + BI_W))));
+      c->bpar.max_out_it = c->cfg.max_out_it;
+      c->bpar.max_theta_it = c->cfg.max_theta_it;
+      c->bpar.max_bias_it = c->cfg.max_bias_it;
+      c->bpar.bias_tol = c->cfg.bias_tol;
+      CU(cudaFuncSetAttribute(em_bias_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CU(cudaEventRecord(c->ev[2], st));
+      em_bias_kernel<<<(unsigned)c->n_loci, BI_NT, smem, st>>>(c->dp, c->bpar, (int)c->n_loci);
+      CU(cudaGetLastError());
+      CU(cudaEventRecord(c->ev[3], st));
+      fpkm_sum_kernel<<<1, 1024, 0, st>>>(dp.locus_fpkm, c->n_loci, c->d_fpkm_sum);
+      CU(cudaGetLastError());
+      CU(cudaEventRecord(c->ev[4], st));
+      CU(cudaStreamSynchronize(st));
+      float ms_ = 0;
+      CU(cudaEventElapsedTime(&ms_, c->ev[2], c->ev[4]));
+      c->stats.solve_ms = ms_;
+      CU(cudaEventElapsedTime(&ms_, c->ev[2], c->ev[3]));
+      c->stats.em_ms = ms_;
+      c->stats.grid_em_ms = 0;
+      c->stats.kernel_launches = 2;
+      c->launch_stats.clear();
+      c->locus_launch.assign(c->n_loci, -1);
+      c->solved = true;
+      c->downloaded = false;
+      return SBQ_SUCCESS;
+   }
    CU(cudaEventRecord(c->ev[2], st));
    CU(cudaEventRecord(c->ev_fork, st));
    int used_side = 0;
@@ -845,6 +912,34 @@ int sbq_results(sbq_ctx* c, double* theta, double* fpkm, double* frac, double* t
 int sbq_get_stats(const sbq_ctx* c, sbq_stats* out) {
    if (!c || !out) return SBQ_ERR_INVALID;
    *out = c->stats;
+   return SBQ_SUCCESS;
+}
+
+int sbq_set_covariates(sbq_ctx* c, const double* x, int64_t n_row, int32_t n_cov) {
+   if (!c || n_cov < 0 || n_cov > BI_MAX_COV || (n_cov > 0 && !x)) return SBQ_ERR_INVALID;
+   std::lock_guard<std::mutex> lk(c->mu);
+   if (n_row != c->n_row) return fail(c, SBQ_ERR_INVALID, "covariates for %lld rows, %lld rows queued", (long long)n_row, (long long)c->n_row);
+   cudaSetDevice(c->device);
+   c->h_cov.clear();
+   if (!c->h_cov.append(x, (size_t)n_row * n_cov)) return fail(c, SBQ_ERR_NOMEM, "pinned staging");
+   c->n_cov = n_cov;
+   c->have_cov = true;
+   c->resident = c->solved = c->downloaded = false;
+   return SBQ_SUCCESS;
+}
+
+int sbq_bias_results(sbq_ctx* c, double* beta, int32_t* outer_iters) {
+   if (!c) return SBQ_ERR_INVALID;
+   std::lock_guard<std::mutex> lk(c->mu);
+   CU(cudaSetDevice(c->device));
+   if (c->cfg.bias_mode != 1 || !c->solved) return fail(c, SBQ_ERR_STATE, "sbq_bias_results needs a solved bias-mode batch");
+   const size_t K = (size_t)c->n_cov, nl = (size_t)c->n_loci;
+   if (!c->r_beta.reserve(nl * K + 1) || !c->r_outer.reserve(nl)) return fail(c, SBQ_ERR_NOMEM, "pinned result buffers");
+   if (K) CU(cudaMemcpyAsync(c->r_beta.p, c->bpar.beta, nl * K * 8, cudaMemcpyDeviceToHost, c->stream));
+   CU(cudaMemcpyAsync(c->r_outer.p, c->bpar.outer, nl * 4, cudaMemcpyDeviceToHost, c->stream));
+   CU(cudaStreamSynchronize(c->stream));
+   if (beta && K) memcpy(beta, c->r_beta.p, nl * K * 8);
+   if (outer_iters) memcpy(outer_iters, c->r_outer.p, nl * 4);
    return SBQ_SUCCESS;
 }
 

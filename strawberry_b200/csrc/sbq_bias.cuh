@@ -1,0 +1,293 @@
+// sbq_bias.cuh - bias-corrected EM (bias_mode = 1): theta-EM, bias-weight update and both convergence tests fused
+// in one persistent kernel, one CTA per locus.
+//
+// THE REFERENCE HAS NO BIAS IMPLEMENTATION (src/bias.cpp is entirely commented out, EmSolver's bias members and the
+// 4-argument init() are never defined or read). What runs here is OUR definition, documented in
+// DESIGN.md section 7 and restated on the CPU by the test oracle (orc_em_bias_csr) - parity is against that
+// restatement only ("parity unpinned" with respect to the reference). It reuses the constants the reference declares
+// for the purpose (include/estimate.hpp:237-242): <= 100 outer rounds, <= 5000 theta iterations, <= 10 bias
+// iterations, bias change limit 1e-2.
+//
+//   row weight   w_i = exp(clamp(beta . x_i, +-30)),  x_i = the row's covariates (gc, gc^2, gc^3, log len, ...)
+//   model        F_ij = alpha_ij w_i, column-normalised over the kept rows: s_j = sum_i alpha_ij w_i
+//   outer round  (1) theta-EM with beta fixed until ||theta' - theta||_2 < theta_tol (theta advanced);
+//                (2) Newton steps of the Poisson log-linear fit n_i ~ w_i d_i, d_i = sum_j alpha_ij theta_j / s_j fixed:
+//                    g = sum_i (n_i - mu_i) x_i,  H = sum_i mu_i x_i x_i^T (+ ridge),  beta += H^-1 g,
+//                    until ||delta beta||_2 < bias_tol;
+//                (3) stop when beta moved less than bias_tol in this round.
+#pragma once
+#include "sbq_kernels.cuh"
+
+namespace sbq {
+
+constexpr int BI_NT = 256;
+constexpr int BI_W = BI_NT / 32;
+constexpr int BI_MAX_COV = 6;
+
+struct BiasParams {
+   const double* x;      // [n_row][n_cov] covariates, row-major over the whole batch
+   double* w;            // [n_row] scratch: row weights
+   double* d;            // [n_row] scratch: row normalisers of the last theta
+   double* beta;         // [n_loci][n_cov] out
+   int32_t* outer;       // [n_loci] out: outer rounds executed
+   int n_cov, max_out_it, max_theta_it, max_bias_it;
+   double bias_tol;
+};
+
+__host__ __device__ inline size_t bias_smem_bytes(int T) { return ((size_t)4 * T + (size_t)BI_W * T) * sizeof(double); }
+
+// warp-per-row pass; MODE 0: acc[col] += alpha * w_i (column sums of the biased model)
+//                    MODE 1: E/M step with th[] (acc[col] += alpha th r_i), flags zero denominators
+//                    MODE 2: d_i = sum alpha th  -> dbuf[i]
+template <int MODE>
+__device__ __forceinline__ void bias_row_pass(const DevParams& p, const int64_t* __restrict__ rp, const int32_t* neff, int R, const double* th,
+                                              double* my_acc, const double* wbuf, double* dbuf, int& zero) {
+   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   for (int i = warp; i < R; i += BI_W) {
+      const int ne = neff[i];
+      if (ne < 0) { if (MODE == 2 && lane == 0) dbuf[i] = 0.0; continue; }
+      const int64_t k0 = rp[i], k1 = rp[i + 1];
+      if (MODE == 0) {
+         const double wi = wbuf[i];
+         for (int64_t k = k0 + lane; k < k1; k += 32) my_acc[p.col[k]] += p.alpha[k] * wi;
+      } else {
+         double d = 0.0;
+         for (int64_t k = k0 + lane; k < k1; k += 32) d += p.alpha[k] * th[p.col[k]];
+         d = warp_sum(d);
+         if (MODE == 2) {
+            if (lane == 0) dbuf[i] = d;
+         } else {
+            if (d == 0) { zero = 1; continue; }
+            const double r = (double)ne / d;
+            for (int64_t k = k0 + lane; k < k1; k += 32) { const int c = p.col[k]; my_acc[c] += p.alpha[k] * th[c] * r; }
+         }
+      }
+   }
+}
+
+__global__ void __launch_bounds__(BI_NT)
+em_bias_kernel(DevParams p, BiasParams bp, int n_loci) {
+   const int l = blockIdx.x;
+   if (l >= n_loci) return;
+   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+   const int K = bp.n_cov;
+   const int64_t r0 = p.loc_row_off[l];
+   const int R = (int)(p.loc_row_off[l + 1] - r0);
+   const int64_t t0 = p.loc_iso_off[l];
+   const int T = (int)(p.loc_iso_off[l + 1] - t0);
+   extern __shared__ double smem[];
+   double* th = smem;
+   double* cur = th + T;
+   double* nxt = cur + T;
+   double* sdiv = nxt + T;
+   double* acc = sdiv + T;   // [BI_W][T]
+   __shared__ double red[BI_NT / 32];
+   __shared__ double s_beta[BI_MAX_COV], s_dbeta[BI_MAX_COV], s_gh[BI_MAX_COV + BI_MAX_COV * BI_MAX_COV];
+   __shared__ double s_n2;
+   const int64_t* __restrict__ rp = p.row_ptr + r0;
+   int32_t* neff = p.neff + r0;
+   double* wbuf = bp.w + r0;
+   double* dbuf = bp.d + r0;
+   const double* __restrict__ X = bp.x + (size_t)r0 * K;
+   double* my_acc = acc + (size_t)warp * T;
+
+   auto reduce_acc = [&](double* out) {   // fixed-order sum over the warp-private accumulators
+      for (int j = tid; j < T; j += BI_NT) {
+         double s = 0.0;
+         for (int w = 0; w < BI_W; ++w) { s += acc[(size_t)w * T + j]; acc[(size_t)w * T + j] = 0.0; }
+         out[j] = s;
+      }
+   };
+
+   // ---- setup: total, row filter, unit weights
+   long long tot = 0;
+   int kept = 0;
+   for (int x = tid; x < BI_W * T; x += BI_NT) acc[x] = 0.0;
+   for (int i = warp; i < R; i += BI_W) {
+      const int64_t k0 = rp[i], k1 = rp[i + 1];
+      bool keep = false;
+      for (int64_t k = k0 + lane; k < k1; k += 32) keep |= p.alpha[k] > p.row_eps;
+      keep = __any_sync(0xffffffffu, keep);
+      if (lane == 0) {
+         const int n = p.count[r0 + i];
+         neff[i] = keep ? n : -1;
+         wbuf[i] = 1.0;
+         tot += n;
+         kept += keep;
+      }
+   }
+   if (tid < BI_MAX_COV) s_beta[tid] = 0.0;
+   const double total = block_sum<BI_NT>((double)tot, red);
+   const double kept_all = block_sum<BI_NT>((double)kept, red);
+   const double theta0 = total / (double)T;
+   for (int j = tid; j < T; j += BI_NT) cur[j] = theta0;
+   __syncthreads();
+
+   int status = LOCUS_ITER_CAP, iters = 0, outer = 0;
+   if (kept_all == 0) {
+      status = LOCUS_NO_ROWS;
+   } else {
+      for (int out = 0; out < bp.max_out_it && status == LOCUS_ITER_CAP; ++out) {
+         outer = out + 1;
+         int zero = 0;
+         bias_row_pass<0>(p, rp, neff, R, th, my_acc, wbuf, dbuf, zero);
+         __syncthreads();
+         reduce_acc(sdiv);
+         __syncthreads();
+         // (1) theta-EM with the current bias
+         for (int it = 0; it < bp.max_theta_it; ++it) {
+            ++iters;
+            for (int j = tid; j < T; j += BI_NT) th[j] = sdiv[j] != 0 ? cur[j] / sdiv[j] : 0.0;
+            __syncthreads();
+            bias_row_pass<1>(p, rp, neff, R, th, my_acc, wbuf, dbuf, zero);
+            zero = __syncthreads_or(zero);
+            reduce_acc(nxt);
+            double d2 = 0.0;
+            for (int j = tid; j < T; j += BI_NT) { const double df = nxt[j] - cur[j]; d2 += df * df; }
+            d2 = block_sum<BI_NT>(d2, red);
+            if (zero) { status = LOCUS_ZERO_DENOM; break; }
+            for (int j = tid; j < T; j += BI_NT) cur[j] = nxt[j];
+            __syncthreads();
+            if (sqrt(d2) < p.tol) break;
+         }
+         if (status == LOCUS_ZERO_DENOM) break;
+         if (K == 0) { status = LOCUS_OK; break; }
+         // (2) bias-weight update: Newton steps on beta with d_i fixed
+         for (int j = tid; j < T; j += BI_NT) th[j] = sdiv[j] != 0 ? cur[j] / sdiv[j] : 0.0;
+         __syncthreads();
+         bias_row_pass<2>(p, rp, neff, R, th, my_acc, wbuf, dbuf, zero);
+         double bprev[BI_MAX_COV];
+         for (int a = 0; a < BI_MAX_COV; ++a) bprev[a] = a < K ? s_beta[a] : 0.0;
+         __syncthreads();
+         for (int nb = 0; nb < bp.max_bias_it; ++nb) {
+            double g[BI_MAX_COV], H[BI_MAX_COV * (BI_MAX_COV + 1) / 2];
+#pragma unroll
+            for (int a = 0; a < BI_MAX_COV; ++a) g[a] = 0.0;
+#pragma unroll
+            for (int a = 0; a < BI_MAX_COV * (BI_MAX_COV + 1) / 2; ++a) H[a] = 0.0;
+            for (int i = tid; i < R; i += BI_NT) {
+               const int ne = neff[i];
+               if (ne < 0) continue;
+               const double mu = wbuf[i] * dbuf[i];
+               const double res = (double)ne - mu;
+               int h = 0;
+#pragma unroll
+               for (int a = 0; a < BI_MAX_COV; ++a) {
+                  const double xa = a < K ? X[(size_t)i * K + a] : 0.0;
+                  g[a] += res * xa;
+#pragma unroll
+                  for (int b = a; b < BI_MAX_COV; ++b) {
+                     const double xb = b < K ? X[(size_t)i * K + b] : 0.0;
+                     H[h++] += mu * xa * xb;
+                  }
+               }
+            }
+            {
+               int h = 0;
+#pragma unroll
+               for (int a = 0; a < BI_MAX_COV; ++a) {
+                  const double ga = block_sum<BI_NT>(g[a], red);
+                  if (tid == 0) s_gh[a] = ga;
+#pragma unroll
+                  for (int b = a; b < BI_MAX_COV; ++b) {
+                     const double hab = block_sum<BI_NT>(H[h++], red);
+                     if (tid == 0) { s_gh[BI_MAX_COV + a * BI_MAX_COV + b] = hab; s_gh[BI_MAX_COV + b * BI_MAX_COV + a] = hab; }
+                  }
+               }
+            }
+            if (tid == 0) {
+               // K x K solve with a small ridge (Gaussian elimination with partial pivoting, like the restatement)
+               double A[BI_MAX_COV * BI_MAX_COV], v[BI_MAX_COV];
+               double tr = 0.0;
+               for (int a = 0; a < K; ++a) tr += s_gh[BI_MAX_COV + a * BI_MAX_COV + a];
+               for (int a = 0; a < K; ++a) {
+                  v[a] = s_gh[a];
+                  for (int b = 0; b < K; ++b) A[a * K + b] = s_gh[BI_MAX_COV + a * BI_MAX_COV + b] + (a == b ? 1e-9 * tr + 1e-12 : 0.0);
+               }
+               bool ok = true;
+               for (int c = 0; c < K && ok; ++c) {
+                  int piv = c;
+                  for (int r = c + 1; r < K; ++r)
+                     if (fabs(A[r * K + c]) > fabs(A[piv * K + c])) piv = r;
+                  if (A[piv * K + c] == 0.0) { ok = false; break; }
+                  if (piv != c) {
+                     for (int k = 0; k < K; ++k) { const double t = A[c * K + k]; A[c * K + k] = A[piv * K + k]; A[piv * K + k] = t; }
+                     const double t = v[c]; v[c] = v[piv]; v[piv] = t;
+                  }
+                  for (int r = c + 1; r < K; ++r) {
+                     const double f = A[r * K + c] / A[c * K + c];
+                     for (int k = c; k < K; ++k) A[r * K + k] -= f * A[c * K + k];
+                     v[r] -= f * v[c];
+                  }
+               }
+               double n2 = -1.0;
+               if (ok) {
+                  for (int c = K - 1; c >= 0; --c) {
+                     double s = v[c];
+                     for (int k = c + 1; k < K; ++k) s -= A[c * K + k] * v[k];
+                     v[c] = s / A[c * K + c];
+                  }
+                  n2 = 0.0;
+                  for (int a = 0; a < K; ++a) { s_beta[a] += v[a]; n2 += v[a] * v[a]; }
+               }
+               s_n2 = n2;
+            }
+            __syncthreads();
+            const double n2 = s_n2;
+            if (n2 < 0) break;   // singular system: keep beta
+            for (int i = tid; i < R; i += BI_NT) {
+               double e = 0.0;
+               for (int a = 0; a < K; ++a) e += s_beta[a] * X[(size_t)i * K + a];
+               e = e > 30.0 ? 30.0 : (e < -30.0 ? -30.0 : e);
+               wbuf[i] = exp(e);
+            }
+            __syncthreads();
+            if (sqrt(n2) < bp.bias_tol) break;
+         }
+         // (3) outer convergence on beta
+         double m2 = 0.0;
+         for (int a = 0; a < K; ++a) m2 += (s_beta[a] - bprev[a]) * (s_beta[a] - bprev[a]);
+         __syncthreads();
+         if (sqrt(m2) < bp.bias_tol) status = LOCUS_OK;
+      }
+   }
+
+   // ---- outputs + epilogue (same tail as the other tiers, src/estimate.cpp:310-356)
+   const bool uniform = status == LOCUS_ZERO_DENOM || status == LOCUS_NO_ROWS;
+   double fsum = 0.0;
+   for (int j = tid; j < T; j += BI_NT) {
+      const double tj = uniform ? theta0 : cur[j];
+      bool na = false;
+      double f = 0.0;
+      if (status != LOCUS_NO_ROWS) f = iso_fpkm(p, tj, p.iso_len[t0 + j], na);
+      p.theta[t0 + j] = tj;
+      p.fpkm[t0 + j] = f;
+      th[j] = na ? -1.0 : 0.0;
+      fsum += f;
+   }
+   fsum = block_sum<BI_NT>(fsum, red);
+   double ksum = 0.0;
+   for (int j = tid; j < T; j += BI_NT) {
+      const bool na = th[j] < 0;
+      const double f = p.fpkm[t0 + j];
+      double fr = 0.0;
+      int kp = 0;
+      if (status != LOCUS_NO_ROWS) {
+         if (!na) fr = f / fsum;
+         kp = !(fr < p.min_frac) ? (na ? -1 : 1) : 0;
+      }
+      p.frac[t0 + j] = fr;
+      p.keep[t0 + j] = kp;
+      if (kp != 0) ksum += f;
+   }
+   ksum = block_sum<BI_NT>(ksum, red);
+   if (tid == 0) {
+      p.iters[l] = iters;
+      p.status[l] = status;
+      p.locus_fpkm[l] = ksum;
+      bp.outer[l] = outer;
+      for (int a = 0; a < K; ++a) bp.beta[(size_t)l * K + a] = s_beta[a];
+   }
+}
+
+}  // namespace sbq
