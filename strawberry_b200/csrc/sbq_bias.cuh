@@ -82,7 +82,7 @@ em_bias_kernel(DevParams p, BiasParams bp, int n_loci) {
    double* sdiv = nxt + T;
    double* acc = sdiv + T;   // [BI_W][T]
    __shared__ double red[BI_NT / 32];
-   __shared__ double s_beta[BI_MAX_COV], s_dbeta[BI_MAX_COV], s_gh[BI_MAX_COV + BI_MAX_COV * BI_MAX_COV];
+   __shared__ double s_beta[BI_MAX_COV], s_gh[BI_MAX_COV + BI_MAX_COV * BI_MAX_COV];
    __shared__ double s_n2;
    const int64_t* __restrict__ rp = p.row_ptr + r0;
    int32_t* neff = p.neff + r0;

@@ -394,9 +394,12 @@ struct ResidentSlice {
 };
 
 // lanes per row / column: the largest power of two <= 32 that still gives every item its own lane group
+#ifndef SBQ_MIN_LANES
+#define SBQ_MIN_LANES 1
+#endif
 __device__ __forceinline__ int lanes_for(int items, int nt) {
    int l = 32;
-   while (l > 1 && (long long)items * l > nt) l >>= 1;
+   while (l > SBQ_MIN_LANES && (long long)items * l > nt) l >>= 1;
    return l;
 }
 

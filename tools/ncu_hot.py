@@ -12,7 +12,7 @@ ix = {h: i for i, h in enumerate(hdr)}
 stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 data = []
 for n, r in enumerate(rows[2:]):
-    if len(r) < len(hdr):
+    if len(r) < len(hdr) or not r[ix["# Samples"]].strip().isdigit():
         continue
     data.append((int(r[ix["# Samples"]] or 0), n, r))
 total = sum(d[0] for d in data)
