@@ -62,6 +62,7 @@ __device__ __forceinline__ void bias_row_pass(const DevParams& p, const int64_t*
             for (int64_t k = k0 + lane; k < k1; k += 32) { const int c = p.col[k]; my_acc[c] += p.alpha[k] * th[c] * r; }
          }
       }
+      __syncwarp();   // the warp's next row may touch the same accumulator column from another lane
    }
 }
 

@@ -105,6 +105,7 @@ __device__ __forceinline__ void grid_row_pass(const DevParams& p, const int64_t*
                         if (c[q][e] >= 0) my[c[q][e]] += a[q][e];
                   }
                }
+               __syncwarp();
             }
          } else {
             double t[GT_RU][GT_EPL], d[GT_RU];
@@ -132,6 +133,7 @@ __device__ __forceinline__ void grid_row_pass(const DevParams& p, const int64_t*
 #pragma unroll
                for (int e = 0; e < GT_EPL; ++e)
                   if (c[q][e] >= 0) my[c[q][e]] += a[q][e] * t[q][e] * r;
+               __syncwarp();   // the next row may touch the same accumulator column from another lane
             }
          }
       } else {
@@ -157,8 +159,10 @@ __device__ __forceinline__ void grid_row_pass(const DevParams& p, const int64_t*
                   my[cc] += al[k] * th[cc] * r;
                }
             }
+            __syncwarp();
          }
       }
+      __syncwarp();
    }
 }
 

@@ -269,6 +269,7 @@ __device__ __forceinline__ void g4_consume(const DevParams& p, const unsigned sh
                      if (a[q][1] != 0.0) my[cc[q][1]] += a[q][1];
                   }
                }
+               __syncwarp();   // the second row of the pair may touch the same accumulator column from another lane
             }
          } else {
             double t[2][G4_EPL], d[2];
@@ -296,6 +297,7 @@ __device__ __forceinline__ void g4_consume(const DevParams& p, const unsigned sh
                const double rr = __shfl_sync(0xffffffffu, rmine, 16 * q);
                if (a[q][0] != 0.0) my[cc[q][0]] += a[q][0] * t[q][0] * rr;
                if (a[q][1] != 0.0) my[cc[q][1]] += a[q][1] * t[q][1] * rr;
+               __syncwarp();   // row 1 of the pair may touch the same accumulator column from another lane
             }
          }
       } else {

@@ -342,6 +342,7 @@ __device__ __forceinline__ void cluster_setup_pass(const Rows& rows, const int32
       if (valid && lg == 0) { rows.set_ne(i, keep ? n : -1); tot += n; kept += keep; }
       if (keep)
          for (unsigned k = k0 + lg; k < k1; k += LPR) my_acc[rows.c(k)] += rows.a(k);
+      __syncwarp();   // the next row of this group may touch the same accumulator column from another lane
    }
 }
 
@@ -369,6 +370,7 @@ __device__ __forceinline__ void cluster_em_pass(const Rows& rows, int nrows, int
             for (unsigned k = a0 + lg; k < b0; k += LPR) { const int c = rows.c(k); my_acc[c] += rows.a(k) * th[c] * r; }
          }
       }
+      __syncwarp();   // row i1 of the same group may share columns with row i0
       if (ne1 >= 0) {
          if (d1 == 0) zero = 1;
          else {
@@ -376,6 +378,7 @@ __device__ __forceinline__ void cluster_em_pass(const Rows& rows, int nrows, int
             for (unsigned k = a1 + lg; k < b1; k += LPR) { const int c = rows.c(k); my_acc[c] += rows.a(k) * th[c] * r; }
          }
       }
+      __syncwarp();   // the next rows of this group may touch the same accumulator columns from other lanes
    }
 }
 
