@@ -157,3 +157,55 @@ def test_full_size_config2_properties(q):
     q.download()
     again = q.results()
     assert np.array_equal(res["theta"], again["theta"]) and np.array_equal(res["iters"], again["iters"])
+
+
+def test_full_size_giant_locus_properties(q):
+    """BASELINE configs[3] shape at full per-locus size (1 M rows x ~48 non-zeros, T ~ U{500..800}; CSR 0.58 GB > L2)
+    through the TMA grid kernel: oracle-free properties, plus agreement with the cluster-tier streaming path."""
+    b = synth.giant(n_loci=1, rows_per_locus=1_000_000, seed=4)
+    qq = q
+    qq.clear()
+    qq.set_plan(0, 0)
+    qq.submit_flat(b)
+    qq.run(b["total_mapped_reads"])
+    res = qq.results()
+    st = qq.stats()
+    assert st["loci_grid"] == 1 and res["status"][0] == 0 and 1 < res["iters"][0] < 1000
+    # every row is kept (alpha > 1e-5) so the EM conserves the full mass
+    assert abs(res["theta"].sum() - 1_000_000) < 1e-6 * 1_000_000
+    assert abs(res["frac"].sum() - 1.0) < 1e-9 and abs(res["tpm"].sum() - 1e6) < 1e-3
+    # bit-reproducible: the resident batch solved again gives identical bits (fixed-shape reductions, no atomics)
+    qq.solve(b["total_mapped_reads"])
+    qq.finalize_tpm(qq.fpkm_sum())
+    qq.download()
+    again = qq.results()
+    assert np.array_equal(res["theta"], again["theta"]) and again["iters"][0] == res["iters"][0]
+    # fixed point: theta is the previous iterate of a converged run, so one more EM step moves it by < tol
+    T = int(b["loc_iso_off"][1])
+    rows = np.repeat(np.arange(1_000_000), np.diff(b["row_ptr"]))
+    s = np.bincount(b["col"], weights=b["alpha"], minlength=T)
+    th = res["theta"] / s
+    d = np.bincount(rows, weights=b["alpha"] * th[b["col"]], minlength=1_000_000)
+    nxt = np.bincount(b["col"], weights=b["alpha"] * th[b["col"]] / d[rows], minlength=T)
+    assert np.linalg.norm(nxt - res["theta"]) < 1e-2
+
+
+def test_config5_shape_with_low_fraction_filter(oracle_mod):
+    """BASELINE configs[4] shape: 60 k loci, 1e8 fragments, assembly-mode default min_iso_frac = 0.01."""
+    b = synth.human_shaped(n_loci=60_000, total_fragments=100_000_000, seed=5)
+    res = run_gpu(None, b, min_iso_frac=0.01)
+    assert res["stats"]["n_loci"] == 60_000 and int(b["count"].sum()) == 100_000_000
+    kept = res["keep"] != 0
+    assert (~kept).any() and (res["frac"][kept] >= 0.01).all()
+    live = np.repeat(res["status"] != 3, np.diff(b["loc_iso_off"]))
+    assert (res["frac"][~kept & live & np.isfinite(res["frac"])] < 0.01).all()
+    assert abs(np.nansum(res["tpm"][kept]) - 1e6) < 1e-3
+    # spot-check 300 loci against the oracle
+    idx = np.arange(0, 60_000, 200)
+    from strawberry_b200 import partition
+    sub, isos = partition.take(b, idx)
+    ora = oracle_mod.quantify_batch(sub, b["total_mapped_reads"], min_iso_frac=0.01)
+    assert np.array_equal(res["iters"][idx], ora["iters"]) and np.array_equal(res["status"][idx], ora["status"])
+    scale = np.maximum(np.abs(ora["theta"]), 1e-9 * np.repeat(np.add.reduceat(sub["count"].astype(np.float64), sub["loc_row_off"][:-1]), np.diff(sub["loc_iso_off"])))
+    assert (np.abs(res["theta"][isos] - ora["theta"]) / np.maximum(scale, 1e-300)).max() < 1e-6
+    assert np.array_equal(res["keep"][isos] != 0, ora["keep"] != 0)
