@@ -153,6 +153,7 @@ struct sbq_ctx {
    double r_fpkm_sum = 0.0;
 
    sbq_stats stats{};
+   bool stats_stale = false;
 };
 
 namespace {
@@ -261,7 +262,7 @@ int plan(sbq_ctx* c) {
    LaunchClass* slot[5] = {};
    std::vector<LaunchClass> tmp;
    tmp.reserve(5);
-   const int64_t grid_min_nnz = 2 * 1000 * 1000;
+   const int64_t grid_min_nnz = 300 * 1000;   // above this a locus is faster on the whole GPU than on a 16-CTA cluster
    for (int64_t l = 0; l < c->n_loci; ++l) {
       const int64_t R = lro[l + 1] - lro[l], T = lio[l + 1] - lio[l];
       const int64_t nnz = rp[lro[l + 1]] - rp[lro[l]];
@@ -850,7 +851,28 @@ int sbq_download(sbq_ctx* c) {
    c->stats.download_ms = ms;
    c->stats.d2h_bytes = (int64_t)ni * 36 + (int64_t)nl * 8 + 8;
 
-   // accounting for the metric: fragments*EM-iters and algorithmic bytes
+   c->stats_stale = true;   // metric accounting (O(rows) on the host) is done lazily by sbq_get_stats
+   c->downloaded = true;
+   return SBQ_SUCCESS;
+}
+
+int sbq_run(sbq_ctx* c, int64_t total_mapped_reads) {
+   int rc = sbq_upload(c);
+   if (rc) return rc;
+   if ((rc = sbq_solve(c, total_mapped_reads))) return rc;
+   double s = 0.0;
+   if ((rc = sbq_fpkm_sum(c, &s))) return rc;
+   if ((rc = sbq_finalize_tpm(c, s))) return rc;
+   return sbq_download(c);
+}
+
+} // extern "C" (reopened below)
+
+// Accounting for the benchmark metric: fragments*EM-iters and algorithmic bytes. O(rows) on the
+// host, so it is evaluated lazily by sbq_get_stats / sbq_get_launch_stats rather than inside sbq_download.
+static void account(sbq_ctx* c) {
+   if (!c->stats_stale || !c->downloaded) return;
+   const size_t nl = (size_t)c->n_loci;
    const int64_t *lro = loc_row_off(c), *lio = loc_iso_off(c), *rp = row_ptr(c);
    const int32_t* cnt = countp(c);
    std::vector<char> is_grid(nl, 0);
@@ -880,19 +902,10 @@ int sbq_download(sbq_ctx* c) {
    c->stats.frag_iters = frag_iters;
    c->stats.alg_bytes = alg;
    c->stats.grid_alg_bytes = galg;
-   c->downloaded = true;
-   return SBQ_SUCCESS;
+   c->stats_stale = false;
 }
 
-int sbq_run(sbq_ctx* c, int64_t total_mapped_reads) {
-   int rc = sbq_upload(c);
-   if (rc) return rc;
-   if ((rc = sbq_solve(c, total_mapped_reads))) return rc;
-   double s = 0.0;
-   if ((rc = sbq_fpkm_sum(c, &s))) return rc;
-   if ((rc = sbq_finalize_tpm(c, s))) return rc;
-   return sbq_download(c);
-}
+extern "C" {
 
 int sbq_results(sbq_ctx* c, double* theta, double* fpkm, double* frac, double* tpm, int32_t* keep, int32_t* iters, int32_t* status) {
    if (!c) return SBQ_ERR_INVALID;
@@ -909,8 +922,13 @@ int sbq_results(sbq_ctx* c, double* theta, double* fpkm, double* frac, double* t
    return SBQ_SUCCESS;
 }
 
-int sbq_get_stats(const sbq_ctx* c, sbq_stats* out) {
-   if (!c || !out) return SBQ_ERR_INVALID;
+int sbq_get_stats(const sbq_ctx* cc, sbq_stats* out) {
+   if (!cc || !out) return SBQ_ERR_INVALID;
+   sbq_ctx* c = const_cast<sbq_ctx*>(cc);
+   {
+      std::lock_guard<std::mutex> lk(c->mu);
+      account(c);
+   }
    *out = c->stats;
    return SBQ_SUCCESS;
 }
@@ -943,8 +961,13 @@ int sbq_bias_results(sbq_ctx* c, double* beta, int32_t* outer_iters) {
    return SBQ_SUCCESS;
 }
 
-int sbq_get_launch_stats(const sbq_ctx* c, sbq_launch_stat* out, int cap) {
-   if (!c || (!out && cap > 0)) return SBQ_ERR_INVALID;
+int sbq_get_launch_stats(const sbq_ctx* cc, sbq_launch_stat* out, int cap) {
+   if (!cc || (!out && cap > 0)) return SBQ_ERR_INVALID;
+   sbq_ctx* c = const_cast<sbq_ctx*>(cc);
+   {
+      std::lock_guard<std::mutex> lk(c->mu);
+      account(c);
+   }
    const int n = (int)c->launch_stats.size();
    for (int i = 0; i < n && i < cap; ++i) out[i] = c->launch_stats[i];
    return n;

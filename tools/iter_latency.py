@@ -27,7 +27,7 @@ def one_locus(T, R, k_mean, seed=0):
 ITERS = 400
 q = api.Quantifier(max_iter=ITERS, theta_tol=0.0)
 shapes = [(4, 4, 2, 1, 0), (4, 4, 2, 2, 1), (8, 30, 3, 1, 0), (30, 150, 12, 1, 0), (30, 150, 12, 2, 1), (34, 101, 13, 2, 1), (60, 300, 20, 2, 1),
-          (60, 300, 20, 2, 2), (145, 1000, 60, 2, 4), (145, 2000, 60, 2, 8), (145, 4362, 63, 2, 16), (200, 3000, 90, 2, 16)]
+          (60, 300, 20, 2, 2), (145, 1000, 60, 2, 4), (145, 2000, 60, 2, 8), (145, 4362, 63, 2, 16), (200, 3000, 90, 2, 16), (145, 4362, 63, 3, 0), (200, 3000, 90, 3, 0), (145, 2000, 60, 3, 0), (500, 20000, 25, 3, 0), (500, 20000, 25, 2, 16)]
 for T, R, k, tier, cs in shapes:
     b = one_locus(T, R, k)
     q.clear()
