@@ -571,9 +571,6 @@ int sbq_upload(sbq_ctx* c) {
    std::lock_guard<std::mutex> lk(c->mu);
    CU(cudaSetDevice(c->device));
    if (c->n_loci == 0) return fail(c, SBQ_ERR_STATE, "nothing submitted");
-   int rc = plan(c);
-   if (rc) return rc;
-
    // +64 B of slack per array: the giant-locus kernel's 16-byte-granular bulk copies may read a few elements past the end
    const size_t sz_lro = align_up((c->n_loci + 1) * sizeof(int64_t)), sz_rp = align_up((c->n_row + 1) * sizeof(int64_t) + 64);
    const size_t sz_col = align_up(c->nnz * sizeof(int32_t) + 64), sz_al = align_up(c->nnz * sizeof(double) + 64);
@@ -583,7 +580,7 @@ int sbq_upload(sbq_ctx* c) {
    const size_t sz_iso_d = align_up(c->n_iso * sizeof(double)), sz_iso_i = align_up(c->n_iso * sizeof(int32_t));
    const size_t sz_loc_i = align_up(c->n_loci * sizeof(int32_t)), sz_loc_d = align_up(c->n_loci * sizeof(double));
    const size_t out_bytes = 4 * sz_iso_d + sz_iso_i + 2 * sz_loc_i + sz_loc_d + 256;
-   if (!c->d_in.reserve(in_bytes) || !c->d_out.reserve(out_bytes) || !c->d_lists.reserve(align_up(c->h_lists.n * sizeof(int32_t)) + 256))
+   if (!c->d_in.reserve(in_bytes) || !c->d_out.reserve(out_bytes) || !c->d_lists.reserve(align_up((size_t)c->n_loci * sizeof(int32_t)) + 256))
       return fail(c, SBQ_ERR_NOMEM, "device allocation failed (%zu MB)", (in_bytes + out_bytes) >> 20);
 
    char* p = (char*)c->d_in.p;
@@ -623,6 +620,14 @@ int sbq_upload(sbq_ctx* c) {
    }
    if (c->n_row) CU(cudaMemcpyAsync(d_cnt, countp(c), c->n_row * sizeof(int32_t), cudaMemcpyHostToDevice, st));
    CU(cudaMemcpyAsync(d_il, iso_lenp(c), c->n_iso * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+   // the tier plan (O(loci) on the host) is made while the DMA engine moves the batch
+   {
+      const int rc = plan(c);
+      if (rc) {
+         cudaStreamSynchronize(st);
+         return rc;
+      }
+   }
    if (c->h_lists.n) CU(cudaMemcpyAsync(c->d_lists_p, c->h_lists.p, c->h_lists.n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
    CU(cudaEventRecord(c->ev[1], st));
    CU(cudaStreamSynchronize(st));   // borrowed host arrays may be released after this returns
