@@ -28,8 +28,8 @@ def parse_gtf(path):
     return out
 
 
-def run(binary, bam, gtf, out, log, threads=1):
-    cmd = [binary, bam, "-g", gtf, "-r", "-o", out, "-T", log, "-p", str(threads)]
+def run(binary, bam, gtf, out, log, threads=1, ctx=None):
+    cmd = [binary, bam, "-g", gtf, "-r", "-o", out, "-T", log, "-p", str(threads)] + (["-f", ctx] if ctx else [])
     subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
 
 
@@ -64,3 +64,36 @@ def test_dropin_binary_matches_reference_binary(tmp_path, threads):
     th_got = sorted(float(x) for x in re.findall(r"has ([0-9.]+) raw read count", outs["sbq"][1]))
     assert len(th_ref) == len(th_got) and len(th_ref) > 0
     assert max(abs(a - b) for a, b in zip(th_ref, th_got)) <= 2e-6 * max(1.0, max(th_ref))
+
+
+def test_fragment_context_tsv_matches_reference(tmp_path):
+    """a18 / SURVEY 8f.3: the -f fragment-context TSV (class coordinates, 12-digit alpha rows, counts, FPKM and frac
+    strings - the input format of the downstream DE tool) written by the integrated binary equals the reference's."""
+    if not all(os.path.exists(b) for b in BINS):
+        pytest.skip("oracle/_ref binaries not built (make -C integration)")
+    sam, gtf, bam = (str(tmp_path / n) for n in ("s.sam", "s.gtf", "s.bam"))
+    samgen.write_dataset(sam, gtf, n_genes=80, seed=9)
+    with open(bam, "wb") as fh:
+        subprocess.run([BINS[2], "view", "-bS", sam], check=True, stdout=fh, stderr=subprocess.DEVNULL)
+    rows = {}
+    for tag, binary in (("ref", BINS[0]), ("sbq", BINS[1])):
+        ctx = str(tmp_path / f"{tag}.tsv")
+        run(binary, bam, gtf, str(tmp_path / f"{tag}f.gtf"), str(tmp_path / f"{tag}f.log"), 1, ctx)
+        rows[tag] = [l.rstrip("\n").split("\t") for l in open(ctx)]
+    ref, got = rows["ref"], rows["sbq"]
+    assert len(ref) == len(got) > 500 and ref[0] == got[0]
+    hdr = ref[0]
+    num_cols = {hdr.index("FPKMs"), hdr.index("conditional_probabilities"), hdr.index("class_probabilities")}
+    for a, b in zip(ref[1:], got[1:]):
+        assert len(a) == len(b)
+        for k, (x, y) in enumerate(zip(a, b)):
+            if k in num_cols:
+                xs, ys = x.split(","), y.split(",")
+                assert len(xs) == len(ys)
+                for u, v in zip(xs, ys):
+                    if u == v:
+                        continue
+                    fu, fv = float(u), float(v)
+                    assert abs(fu - fv) <= 1e-9 * max(abs(fu), 1e-30) + (2e-6 if k != hdr.index("conditional_probabilities") else 0.0), (hdr[k], u, v)
+            else:
+                assert x == y, (hdr[k], x, y)
