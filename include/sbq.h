@@ -93,6 +93,7 @@ typedef struct {
    int64_t frag_iters;                       /* sum over loci of (sum_i n_i) * iters                */
    int64_t alg_bytes;                        /* sum over loci of (12 nnz + 12 R + 16 T) * iters      */
    int64_t grid_alg_bytes;                   /* same, loci solved by the giant-locus kernel only    */
+   double  weights_ms;                       /* GPU class-weight kernel + its descriptor H2D (deferred-weight batches) */
 } sbq_stats;
 
 int  sbq_abi_version(void);

@@ -63,6 +63,8 @@ typedef struct {
    const int32_t* hit_ref_id;    /* Contig::ref_id(); may be NULL (all 0)                         */
    int32_t read_len;             /* ReadTable::read_len_mode()                                   */
    int32_t long_read;            /* long_read_sample: alpha = 1 / L_t (src/estimate.cpp:236-247) */
+   int32_t defer_weights;        /* 1: do not evaluate the alpha sums on the host; emit per-entry descriptors instead */
+                                 /*    (sbq_table_weight_desc) and let sbq_submit_deferred compute alpha on the GPU   */
 } sbq_locus_input;
 
 typedef struct sbq_table sbq_table;
@@ -89,6 +91,29 @@ int  sbq_table_segments(const sbq_table*, uint32_t* seg_left, uint32_t* seg_righ
 int  sbq_table_iso_segments(const sbq_table*, int32_t* iso_seg_ptr, int32_t* iso_seg);
 int  sbq_table_classes(const sbq_table*, int32_t* class_coord_ptr, int32_t* class_coord, int32_t* class_count,
                        float* class_mass, int32_t* class_nfrag);
+
+/* Deferred weights: what the GPU needs to evaluate alpha_ct = sum_fl pdf(fl) * effective_len(fl) / (L_t - fl + 1)
+ * (LocusContext::set_theory_bin_weight, src/estimate.cpp:201-234) for every CSR entry of the table. Entry k's segment
+ * lengths are pool[seg_ptr[k] .. seg_ptr[k] + n_seg[k]); seg_ptr[k] = -1 means alpha[k] is already final (long-read
+ * mode, or a class spanning more than 32 segments). Pointers stay valid until sbq_table_free. */
+typedef struct {
+   int64_t n_entry;
+   const int64_t* seg_ptr;
+   const uint8_t* n_seg;
+   const uint32_t* implicit_mask;   /* bit i set = segment i of the span is implicit (include/isoform.h:363-411) */
+   const int32_t* iso_len;          /* L_t of the entry's isoform */
+   const uint32_t* pool;
+   int64_t n_pool;
+} sbq_weight_desc;
+int  sbq_table_weight_desc(const sbq_table*, sbq_weight_desc* out);
+
+/* GPU weights (the weight half of the class-table build on the device). The insert model and read
+ * length are per context; tables built with defer_weights = 1 are queued like sbq_submit, their alpha is computed by
+ * weights_kernel during sbq_upload. A batch is either all deferred or all host-weighted. sbq_fetch_alpha copies the
+ * device alpha (nnz doubles, CSR order of the batch) back, e.g. to fill ExonBin::_bin_weight_map for -f output. */
+int  sbq_set_insert_model(sbq_ctx*, const sbq_insert_model* model, int32_t read_len);
+int  sbq_submit_deferred(sbq_ctx*, const sbq_table* const* tables, int64_t n_tables);
+int  sbq_fetch_alpha(sbq_ctx*, double* alpha);
 
 /* hit_class[n_hit]: class id of every input hit (the ExonBin whose _frags set it was offered to), -1 for hits
  * that were dropped (ref_id -1) or are compatible with no isoform. */

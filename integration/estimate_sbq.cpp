@@ -94,7 +94,7 @@ void LocusContext::assign_exon_bin(const vector<Contig>& hits, const vector<Geno
                           ins._use_emp ? ins._emp_dist.data() : nullptr, ins._use_emp ? ins._total_reads : 0, ins._mean, ins._sd};
    sbq_locus_input in{(int32_t)_transcripts.size(), iso_ptr.data(), ioff.data(), ilen.data(), icode.data(),
                       (int32_t)hits.size(), hit_ptr.data(), hoff.data(), hlen.data(), hcode.data(), mass.data(), ref_ids.data(),
-                      _read_len, long_read_sample ? 1 : 0};
+                      _read_len, long_read_sample ? 1 : 0, 0};
    sbq_table* tb = nullptr;
    const int rc = sbq_build_locus(&in, &model, &tb);
    if (rc != SBQ_SUCCESS) {

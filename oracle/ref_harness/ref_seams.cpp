@@ -197,7 +197,10 @@ long ref_locus_context(int use_emp, const int* frag_lens, int n_frag_lens, doubl
    }
    os << "],";
 
+   auto t_ctor0 = std::chrono::steady_clock::now();
    LocusContext lc(sample, log, cluster, transcripts);
+   const double ctor_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_ctor0).count();
+   os << "\"ctor_seconds\":" << ctor_seconds << ",";
 
    os << "\"segs\":[";
    for (size_t i = 0; i < lc._exon_segs.size(); ++i) {

@@ -54,7 +54,8 @@ class Stats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int64) for n in ("n_loci", "n_row", "n_iso", "nnz", "loci_warp", "loci_cta", "loci_grid",
                                               "kernel_launches", "h2d_bytes", "d2h_bytes")] + \
                [(n, ctypes.c_double) for n in ("upload_ms", "solve_ms", "download_ms", "em_ms", "grid_em_ms")] + \
-               [(n, ctypes.c_int64) for n in ("em_iters_total", "frag_iters", "alg_bytes", "grid_alg_bytes")]
+               [(n, ctypes.c_int64) for n in ("em_iters_total", "frag_iters", "alg_bytes", "grid_alg_bytes")] + \
+               [("weights_ms", ctypes.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -209,6 +210,26 @@ class Quantifier:
         outer = np.zeros(nl, np.int32)
         self._chk(self._L.sbq_bias_results(self._h, _ptr(beta), _ptr(outer)))
         return beta[:, :self._n_cov], outer
+
+    def set_insert_model(self, model, read_len):
+        """deferred (GPU) weights: the context's insert-size model (builder.Model) and read length"""
+        from . import builder
+        builder._lib()
+        self._model = model
+        self._chk(self._L.sbq_set_insert_model(self._h, ctypes.byref(model.struct), int(read_len)))
+
+    def submit_deferred(self, tables):
+        """tables: builder.TableHandle objects built with defer_weights=True"""
+        from . import builder
+        builder._lib()
+        arr = (ctypes.c_void_p * len(tables))(*[t.handle for t in tables])
+        self._keepalive.append(tables)
+        self._chk(self._L.sbq_submit_deferred(self._h, arr, len(tables)))
+
+    def fetch_alpha(self):
+        out = np.empty(self.stats()["nnz"])
+        self._chk(self._L.sbq_fetch_alpha(self._h, _ptr(out)))
+        return out
 
     def validate(self):
         self._chk(self._L.sbq_validate(self._h))

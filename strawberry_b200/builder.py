@@ -14,7 +14,8 @@ MATCH, INTRON, GAP = 0, 1, 2
 CIG_M, CIG_I, CIG_D, CIG_N, CIG_S = 0, 1, 2, 3, 4
 
 BUILDER_SYMBOLS = ["sbq_build_locus", "sbq_table_free", "sbq_table_locus", "sbq_table_get_dims", "sbq_table_segments",
-                   "sbq_table_iso_segments", "sbq_table_classes", "sbq_table_hit_classes", "sbq_pair_features", "sbq_effective_len", "sbq_insert_pdf"]
+                   "sbq_table_iso_segments", "sbq_table_classes", "sbq_table_hit_classes", "sbq_table_weight_desc",
+                   "sbq_set_insert_model", "sbq_submit_deferred", "sbq_fetch_alpha", "sbq_pair_features", "sbq_effective_len", "sbq_insert_pdf"]
 
 
 class InsertModel(ctypes.Structure):
@@ -27,7 +28,7 @@ class LocusInput(ctypes.Structure):
                 ("iso_feat_len", ctypes.c_void_p), ("iso_feat_code", ctypes.c_void_p), ("n_hit", ctypes.c_int32),
                 ("hit_feat_ptr", ctypes.c_void_p), ("hit_feat_off", ctypes.c_void_p), ("hit_feat_len", ctypes.c_void_p),
                 ("hit_feat_code", ctypes.c_void_p), ("hit_mass", ctypes.c_void_p), ("hit_ref_id", ctypes.c_void_p),
-                ("read_len", ctypes.c_int32), ("long_read", ctypes.c_int32)]
+                ("read_len", ctypes.c_int32), ("long_read", ctypes.c_int32), ("defer_weights", ctypes.c_int32)]
 
 
 class TableDims(ctypes.Structure):
@@ -46,6 +47,9 @@ def _lib():
         L.sbq_table_iso_segments.argtypes = [ctypes.c_void_p] * 3
         L.sbq_table_classes.argtypes = [ctypes.c_void_p] * 6
         L.sbq_table_hit_classes.argtypes = [ctypes.c_void_p] * 2
+        L.sbq_set_insert_model.argtypes = [ctypes.c_void_p, ctypes.POINTER(InsertModel), ctypes.c_int32]
+        L.sbq_submit_deferred.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+        L.sbq_fetch_alpha.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.sbq_pair_features.argtypes = [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                         ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]
@@ -116,7 +120,19 @@ def effective_len(seg_lens, implicit_idx, fl, rl):
     return _lib().sbq_effective_len(_p(s), len(s), _p(im), len(im), int(fl), int(rl))
 
 
-def build_locus(transcripts, hits, *, read_len, model=None, long_read=False, ref_ids=None):
+class TableHandle:
+    """Owns an sbq_table (freed on collection); passed to Quantifier.submit_deferred."""
+
+    def __init__(self, handle):
+        self.handle = handle
+
+    def __del__(self):
+        if self.handle:
+            _lib().sbq_table_free(self.handle)
+            self.handle = None
+
+
+def build_locus(transcripts, hits, *, read_len, model=None, long_read=False, ref_ids=None, defer_weights=False):
     """transcripts: list of feature lists [(code, offset, len), ...]; hits: list of (mass, feature list).
 
     Returns a dict: segs [(l, r)], iso_segs [[seg idx]], iso_len, classes [{coords, count, mass, nfrag}],
@@ -128,7 +144,7 @@ def build_locus(transcripts, hits, *, read_len, model=None, long_read=False, ref
     mass = np.asarray([m for m, _ in hits], np.float64)
     rid = np.asarray(ref_ids, np.int32) if ref_ids is not None else None
     inp = LocusInput(len(transcripts), _p(ip), _p(io), _p(il), _p(ic), len(hits), hp.ctypes.data, _p(ho), _p(hl), _p(hc),
-                     _p(mass), _p(rid) if rid is not None else None, int(read_len), int(long_read))
+                     _p(mass), _p(rid) if rid is not None else None, int(read_len), int(long_read), int(defer_weights))
     h = ctypes.c_void_p()
     rc = L.sbq_build_locus(ctypes.byref(inp), ctypes.byref(model.struct) if model is not None else None, ctypes.byref(h))
     if rc != 0:
@@ -161,6 +177,11 @@ def build_locus(transcripts, hits, *, read_len, model=None, long_read=False, ref
                      for c in range(d.n_class)],
             row_ptr=row_ptr, col=view(loc.col, d.nnz, np.int32), alpha=view(loc.alpha, d.nnz, np.float64),
             count=cnt[:d.n_class].copy(), n_dropped=d.n_dropped_hits, n_iso=d.n_iso, hit_class=hcl[:len(hits)].copy())
-    finally:
+    except BaseException:
+        L.sbq_table_free(h)
+        raise
+    if defer_weights:
+        out["table"] = TableHandle(h)      # alpha in `out` is a placeholder (zeros) until the GPU fills it
+    else:
         L.sbq_table_free(h)
     return out

@@ -16,10 +16,12 @@
 #include <vector>
 
 #include "../../include/sbq.h"
+#include "../../include/sbq_builder.h"
 #include "sbq_kernels.cuh"
 #include "sbq_grid.cuh"
 #include "sbq_grid_tma.cuh"
 #include "sbq_bias.cuh"
+#include "sbq_weights.cuh"
 
 using namespace sbq;
 
@@ -118,6 +120,8 @@ struct sbq_ctx {
    const int32_t *b_col = nullptr, *b_count = nullptr, *b_iso_len = nullptr;
    const double* b_alpha = nullptr;
    int64_t n_loci = 0, n_row = 0, n_iso = 0, nnz = 0;
+   bool in_deferred_submit = false;
+   std::mutex deferred_mu;   // serialises sbq_submit_deferred calls (descriptor order must match CSR order)
 
    // bias mode
    PinnedVec<double> h_cov;
@@ -128,6 +132,19 @@ struct sbq_ctx {
    PinnedVec<double> r_beta;
    PinnedVec<int32_t> r_outer;
    int max_iso_all = 1;
+
+   // deferred (GPU) weights
+   int deferred = 0;                 // 0 = nothing queued yet, 1 = every queued locus is deferred, 2 = host-weighted batch
+   PinnedVec<int64_t> h_wseg;
+   PinnedVec<uint8_t> h_wn;
+   PinnedVec<uint32_t> h_wmask, h_wpool;
+   PinnedVec<int32_t> h_wlen;
+   std::vector<double> model_emp;
+   sbq_insert_model model{};
+   int model_read_len = 0;
+   bool have_model = false;
+   DevBuf d_weights;
+   double weights_ms = 0.0;
 
    // plan
    int force_tier = 0, force_cluster = 0;
@@ -218,6 +235,8 @@ void reset_batch(sbq_ctx* c) {
    c->n_loci = c->n_row = c->n_iso = c->nnz = 0;
    c->have_cov = false;
    c->h_cov.clear();
+   c->deferred = 0;
+   c->h_wseg.clear(); c->h_wn.clear(); c->h_wmask.clear(); c->h_wpool.clear(); c->h_wlen.clear();
    c->resident = c->solved = c->downloaded = false;
 }
 
@@ -442,6 +461,7 @@ void sbq_destroy(sbq_ctx* c) {
    c->r_locus_fpkm.release(); c->r_keep.release(); c->r_iters.release(); c->r_status.release();
    c->d_in.release(); c->d_out.release(); c->d_lists.release(); c->d_grid_scratch.release(); c->d_col16.release(); c->d_bias.release();
    c->h_cov.release(); c->r_beta.release(); c->r_outer.release();
+   c->h_wseg.release(); c->h_wn.release(); c->h_wmask.release(); c->h_wpool.release(); c->h_wlen.release(); c->d_weights.release();
    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
    for (auto& e : c->ev_join) if (e) cudaEventDestroy(e);
@@ -473,6 +493,8 @@ int sbq_submit(sbq_ctx* c, const sbq_locus* loci, int64_t n_loci) {
    if (!c || (!loci && n_loci > 0) || n_loci < 0) return SBQ_ERR_INVALID;
    std::lock_guard<std::mutex> lk(c->mu);
    cudaSetDevice(c->device);
+   if (c->deferred == 1 && !c->in_deferred_submit) return fail(c, SBQ_ERR_STATE, "a batch is either all deferred-weight or all host-weighted");
+   if (!c->in_deferred_submit && n_loci > 0) c->deferred = 2;
    int rc = materialise(c);
    if (rc) return rc;
    if ((rc = ensure_origin(c))) return rc;
@@ -509,6 +531,8 @@ int sbq_submit_flat(sbq_ctx* c, int64_t n_loci, const int64_t* lro, const int64_
    if (!lro || !lio || !rp || !iso_len) return fail(c, SBQ_ERR_INVALID, "null offset array");
    std::lock_guard<std::mutex> lk(c->mu);
    cudaSetDevice(c->device);
+   if (c->deferred == 1) return fail(c, SBQ_ERR_STATE, "a batch is either all deferred-weight or all host-weighted");
+   c->deferred = 2;
    const int64_t rows = lro[n_loci] - lro[0], isos = lio[n_loci] - lio[0];
    if (rows < 0 || isos < n_loci) return fail(c, SBQ_ERR_INVALID, "bad locus offsets");
    const int64_t k0 = rp[lro[0]], k1 = rp[lro[n_loci]];
@@ -636,6 +660,41 @@ int sbq_upload(sbq_ctx* c) {
    c->stats.upload_ms = ms;
    c->stats.h2d_bytes = 2 * (c->n_loci + 1) * 8 + (c->n_row + 1) * 8 + c->nnz * 12 + c->n_row * 4 + c->n_iso * 4 + (int64_t)c->h_lists.n * 4;
    c->stats.n_loci = c->n_loci; c->stats.n_row = c->n_row; c->stats.n_iso = c->n_iso; c->stats.nnz = c->nnz;
+   c->stats.weights_ms = 0.0;
+   if (c->deferred == 1) {
+      // alpha on the GPU: upload the per-entry descriptors and the insert model, one warp per CSR entry
+      if (!c->have_model) return fail(c, SBQ_ERR_STATE, "deferred weights need sbq_set_insert_model()");
+      if ((int64_t)c->h_wseg.n != c->nnz) return fail(c, SBQ_ERR_STATE, "deferred-weight descriptors do not cover the batch");
+      const size_t b_seg = align_up(c->nnz * 8 + 8), b_n = align_up(c->nnz + 8), b_m = align_up(c->nnz * 4 + 8), b_l = align_up(c->nnz * 4 + 8);
+      const size_t b_pool = align_up(c->h_wpool.n * 4 + 8), b_emp = align_up(c->model_emp.size() * 8 + 8);
+      if (!c->d_weights.reserve(b_seg + b_n + b_m + b_l + b_pool + b_emp)) return fail(c, SBQ_ERR_NOMEM, "device allocation failed (weight descriptors)");
+      char* q = (char*)c->d_weights.p;
+      int64_t* d_seg = (int64_t*)q; q += b_seg;
+      uint8_t* d_n = (uint8_t*)q; q += b_n;
+      uint32_t* d_m = (uint32_t*)q; q += b_m;
+      int32_t* d_l = (int32_t*)q; q += b_l;
+      uint32_t* d_pool = (uint32_t*)q; q += b_pool;
+      double* d_emp = (double*)q;
+      cudaStream_t st = c->stream;
+      CU(cudaEventRecord(c->ev[5], st));
+      CU(cudaMemcpyAsync(d_seg, c->h_wseg.p, c->nnz * 8, cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(d_n, c->h_wn.p, c->nnz, cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(d_m, c->h_wmask.p, c->nnz * 4, cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(d_l, c->h_wlen.p, c->nnz * 4, cudaMemcpyHostToDevice, st));
+      if (c->h_wpool.n) CU(cudaMemcpyAsync(d_pool, c->h_wpool.p, c->h_wpool.n * 4, cudaMemcpyHostToDevice, st));
+      if (!c->model_emp.empty()) CU(cudaMemcpyAsync(d_emp, c->model_emp.data(), c->model_emp.size() * 8, cudaMemcpyHostToDevice, st));
+      WeightModel wm{c->model.use_emp, c->model.start_offset, c->model.end_offset, c->model.total_reads, d_emp, c->model.mean, c->model.sd, c->model_read_len};
+      const int blocks = std::max(1, std::min<int>((int)((c->nnz + 7) / 8), c->prop.multiProcessorCount * 16));
+      weights_kernel<<<blocks, 256, 0, st>>>(c->nnz, d_seg, d_n, d_m, d_l, d_pool, wm, const_cast<double*>(c->dp.alpha));
+      CU(cudaGetLastError());
+      CU(cudaEventRecord(c->ev[6], st));
+      CU(cudaStreamSynchronize(st));
+      float wms = 0;
+      CU(cudaEventElapsedTime(&wms, c->ev[5], c->ev[6]));
+      c->weights_ms = wms;
+      c->stats.weights_ms = wms;
+      c->stats.h2d_bytes += (int64_t)(c->nnz * 17 + c->h_wpool.n * 4 + c->model_emp.size() * 8);
+   }
    if (c->cfg.bias_mode == 1) {
       if (!c->have_cov) return fail(c, SBQ_ERR_STATE, "bias_mode = 1 needs sbq_set_covariates() after the last submit");
       const size_t K = (size_t)c->n_cov;
@@ -935,6 +994,63 @@ int sbq_get_stats(const sbq_ctx* cc, sbq_stats* out) {
       account(c);
    }
    *out = c->stats;
+   return SBQ_SUCCESS;
+}
+
+int sbq_set_insert_model(sbq_ctx* c, const sbq_insert_model* model, int32_t read_len) {
+   if (!c || !model || read_len < 1) return SBQ_ERR_INVALID;
+   std::lock_guard<std::mutex> lk(c->mu);
+   c->model = *model;
+   c->model_emp.clear();
+   if (model->use_emp) {
+      if (!model->emp_dist || model->end_offset < model->start_offset) return fail(c, SBQ_ERR_INVALID, "bad empirical insert model");
+      c->model_emp.assign(model->emp_dist, model->emp_dist + (model->end_offset - model->start_offset + 1));
+   }
+   c->model.emp_dist = nullptr;
+   c->model_read_len = read_len;
+   c->have_model = true;
+   c->resident = c->solved = c->downloaded = false;
+   return SBQ_SUCCESS;
+}
+
+int sbq_submit_deferred(sbq_ctx* c, const sbq_table* const* tables, int64_t n_tables) {
+   if (!c || (!tables && n_tables > 0) || n_tables < 0) return SBQ_ERR_INVALID;
+   std::lock_guard<std::mutex> serial(c->deferred_mu);
+   for (int64_t t = 0; t < n_tables; ++t) {
+      sbq_locus L;
+      sbq_weight_desc d;
+      if (!tables[t] || sbq_table_locus(tables[t], &L) || sbq_table_weight_desc(tables[t], &d)) return SBQ_ERR_INVALID;
+      const int64_t nnz = L.row_ptr[L.n_row] - L.row_ptr[0];
+      if (d.n_entry != nnz) return fail(c, SBQ_ERR_INVALID, "table %lld was not built with defer_weights = 1", (long long)t);
+      {
+         std::lock_guard<std::mutex> lk(c->mu);
+         if (c->deferred == 2) return fail(c, SBQ_ERR_STATE, "a batch is either all deferred-weight or all host-weighted");
+         c->deferred = 1;
+         c->in_deferred_submit = true;
+         cudaSetDevice(c->device);
+         const int64_t pool_base = (int64_t)c->h_wpool.n;
+         bool ok = c->h_wseg.reserve(c->h_wseg.n + nnz) && c->h_wn.append(d.n_seg, nnz) && c->h_wmask.append(d.implicit_mask, nnz) &&
+                   c->h_wlen.append(d.iso_len, nnz) && c->h_wpool.append(d.pool, d.n_pool);
+         if (!ok) { c->in_deferred_submit = false; return fail(c, SBQ_ERR_NOMEM, "pinned staging"); }
+         for (int64_t k = 0; k < nnz; ++k) c->h_wseg.p[c->h_wseg.n++] = d.seg_ptr[k] < 0 ? -1 : d.seg_ptr[k] + pool_base;
+      }
+      const int rc = sbq_submit(c, &L, 1);
+      {
+         std::lock_guard<std::mutex> lk(c->mu);
+         c->in_deferred_submit = false;
+      }
+      if (rc) return rc;
+   }
+   return SBQ_SUCCESS;
+}
+
+int sbq_fetch_alpha(sbq_ctx* c, double* alpha) {
+   if (!c || !alpha) return SBQ_ERR_INVALID;
+   std::lock_guard<std::mutex> lk(c->mu);
+   CU(cudaSetDevice(c->device));
+   if (!c->resident) return fail(c, SBQ_ERR_STATE, "sbq_fetch_alpha before sbq_upload");
+   CU(cudaMemcpyAsync(alpha, c->dp.alpha, c->nnz * 8, cudaMemcpyDeviceToHost, c->stream));
+   CU(cudaStreamSynchronize(c->stream));
    return SBQ_SUCCESS;
 }
 

@@ -185,6 +185,12 @@ struct sbq_table {
    std::vector<double> alpha;
    std::vector<int32_t> iso_len;
    std::vector<int32_t> hit_class;   // class of every input hit, -1 = dropped / compatible with nothing
+   // deferred weights (alpha computed on the GPU): per CSR entry the offset of its segment lengths in w_pool (-1 = alpha
+   // is final), their number, the bit mask of implicit segments and the isoform length
+   std::vector<int64_t> w_seg_ptr;
+   std::vector<uint8_t> w_nseg;
+   std::vector<uint32_t> w_mask, w_pool;
+   std::vector<int32_t> w_len;
    int32_t n_dropped = 0;
 };
 
@@ -384,13 +390,15 @@ int sbq_build_locus(const sbq_locus_input* in, const sbq_insert_model* model, sb
    }
 
    // ---- a4 / a5: weights per (isoform, class) (src/estimate.cpp:201-247), gathered per class row afterwards
-   std::vector<std::vector<std::pair<int32_t, double>>> row_entries(R);
+   struct Entry { int32_t t; double w; int64_t seg_ptr; uint8_t nseg; uint32_t mask; };
+   std::vector<std::vector<Entry>> row_entries(R);
    std::vector<uint32_t> seg_lens, implicit;
    for (int t = 0; t < T; ++t) {
       const int32_t* isegs = tb->iso_seg.data() + tb->iso_seg_ptr[t];
       const int nis = tb->iso_seg_ptr[t + 1] - tb->iso_seg_ptr[t];
       for (int32_t cid : iso_classes[t]) {
          double weight;
+         Entry ent{t, 0.0, -1, 0, 0u};
          if (in->long_read) {
             weight = 1.0 / tb->iso_len[t];
          } else {
@@ -417,17 +425,35 @@ int sbq_build_locus(const sbq_locus_input* in, const sbq_insert_model* model, sb
                lmin = std::max(lmin, inner);
             }
             weight = 0.0;
-            for (int fl = lmin; fl <= lmax; ++fl) {
-               const double le_eff = effective_len(seg_lens.data(), nseg, implicit.data(), (int)implicit.size(), fl, in->read_len);
-               weight += insert_pdf(*model, (uint32_t)fl) * le_eff / (tb->iso_len[t] - fl + 1);
+            if (in->defer_weights && nseg <= 32) {
+               // leave the sum to the GPU (weights_kernel): record what it needs
+               ent.seg_ptr = (int64_t)tb->w_pool.size();
+               ent.nseg = (uint8_t)nseg;
+               for (uint32_t x : implicit) ent.mask |= 1u << x;
+               tb->w_pool.insert(tb->w_pool.end(), seg_lens.begin(), seg_lens.end());
+            } else {
+               for (int fl = lmin; fl <= lmax; ++fl) {
+                  const double le_eff = effective_len(seg_lens.data(), nseg, implicit.data(), (int)implicit.size(), fl, in->read_len);
+                  weight += insert_pdf(*model, (uint32_t)fl) * le_eff / (tb->iso_len[t] - fl + 1);
+               }
             }
          }
-         row_entries[cid].emplace_back(t, weight);
+         ent.w = weight;
+         row_entries[cid].push_back(ent);
       }
    }
    tb->row_ptr.assign(1, 0);
    for (int c = 0; c < R; ++c) {
-      for (auto const& e : row_entries[c]) { tb->col.push_back(e.first); tb->alpha.push_back(e.second); }   // t ascending by construction
+      for (auto const& e : row_entries[c]) {   // t ascending by construction
+         tb->col.push_back(e.t);
+         tb->alpha.push_back(e.w);
+         if (in->defer_weights) {
+            tb->w_seg_ptr.push_back(e.seg_ptr);
+            tb->w_nseg.push_back(e.nseg);
+            tb->w_mask.push_back(e.mask);
+            tb->w_len.push_back(tb->iso_len[e.t]);
+         }
+      }
       tb->row_ptr.push_back((int64_t)tb->col.size());
    }
    *out = tb;
@@ -470,6 +496,18 @@ int sbq_table_iso_segments(const sbq_table* t, int32_t* ptr, int32_t* seg) {
    if (!t) return SBQ_ERR_INVALID;
    if (ptr) memcpy(ptr, t->iso_seg_ptr.data(), t->iso_seg_ptr.size() * sizeof(int32_t));
    if (seg) memcpy(seg, t->iso_seg.data(), t->iso_seg.size() * sizeof(int32_t));
+   return SBQ_SUCCESS;
+}
+
+int sbq_table_weight_desc(const sbq_table* t, sbq_weight_desc* out) {
+   if (!t || !out) return SBQ_ERR_INVALID;
+   out->n_entry = (int64_t)t->w_seg_ptr.size();
+   out->seg_ptr = t->w_seg_ptr.data();
+   out->n_seg = t->w_nseg.data();
+   out->implicit_mask = t->w_mask.data();
+   out->iso_len = t->w_len.data();
+   out->pool = t->w_pool.data();
+   out->n_pool = (int64_t)t->w_pool.size();
    return SBQ_SUCCESS;
 }
 

@@ -67,3 +67,47 @@ def test_locus_end_to_end_vs_live_reference(sbq_lib_path, oracle_mod):
         ref = reference_table(oracle_mod, isoforms, hits, rl, spec, seed % 17 == 0)
         check_case(q, isoforms, hits, rl, spec, seed % 17 == 0, ref, f"seed {seed}")
     q.close()
+
+
+def test_gpu_weights_match_host_builder(sbq_lib_path):
+    """SURVEY 8f.1 (weight half of the class-table build on the device): alpha computed by weights_kernel from the
+    builder's per-entry descriptors equals the host builder's alpha, and the EM on top of it gives the same answer."""
+    from strawberry_b200 import api, builder
+    import numpy as np
+    for kind in ("normal", "emp"):
+        rng = np.random.default_rng(5)
+        model = builder.Model.normal(230.0, 45.0) if kind == "normal" else builder.Model.empirical(
+            [int(x) for x in np.clip(rng.normal(230, 45, 400), 60, 600).astype(int)])
+        host_alpha, tables, host_loci = [], [], []
+        n_multi = 0
+        for seed in range(400, 460):
+            isoforms, hits, rl = locusgen.random_locus(seed)
+            if rl != 50:
+                continue                      # one read length per context
+            tfe = [locusgen.transcript_features(ex) for ex in isoforms]
+            feats = [(m, builder.pair_features(l, r)) for m, l, r in hits]
+            ht = builder.build_locus(tfe, feats, read_len=rl, model=model)
+            dt = builder.build_locus(tfe, feats, read_len=rl, model=model, defer_weights=True)
+            assert np.array_equal(ht["col"], dt["col"]) and np.array_equal(ht["count"], dt["count"])
+            host_alpha.append(ht["alpha"])
+            host_loci.append((ht["n_iso"], ht["row_ptr"], ht["col"], ht["alpha"], ht["count"], ht["iso_len"]))
+            tables.append(dt["table"])
+            n_multi += sum(len(c["coords"]) > 4 for c in ht["classes"])
+        assert len(tables) >= 10 and n_multi > 0
+        q = api.Quantifier()
+        q.set_insert_model(model, 50)
+        q.submit_deferred(tables)
+        q.run(100000)
+        gpu = q.results()
+        alpha_gpu = q.fetch_alpha()
+        alpha_host = np.concatenate(host_alpha)
+        rel = np.abs(alpha_gpu - alpha_host) / np.maximum(np.abs(alpha_host), 1e-300)
+        assert rel[alpha_host != 0].max() < 1e-12 and (alpha_gpu[alpha_host == 0] == 0).all(), rel.max()
+        assert q.stats()["weights_ms"] > 0
+        q2 = api.Quantifier()
+        q2.submit(host_loci)
+        q2.run(100000)
+        host = q2.results()
+        assert np.array_equal(gpu["status"], host["status"]) and np.array_equal(gpu["iters"], host["iters"])
+        assert np.allclose(gpu["theta"], host["theta"], rtol=1e-9, atol=1e-9)
+        q.close(), q2.close()
