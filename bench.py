@@ -10,7 +10,7 @@ A step = one pass of the hot path (EM to convergence + FPKM/frac/filter epilogue
 the rank's batch. `value` is timed with the batch resident in HBM (CUDA events inside libsbq on the
 stream the kernels run on); `e2e` is the same work through the public host-buffer call sbq_run from
 page-locked host arrays, H2D and D2H inside the timed region. N > 1: weak scaling - every rank owns a
-full batch (seed 2 + rank); loci are independent so there is no data-path collective, only the scalar
+full copy of the batch (seed 2); loci are independent so there is no data-path collective, only the scalar
 TPM-denominator all-reduce (NCCL) per step.
 """
 import argparse
@@ -176,7 +176,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- workload: BASELINE configs[1], one full batch per rank (weak scaling)
-    batch = synth.human_shaped(seed=2 + rank)
+    batch = synth.human_shaped(seed=2)   # the same 10M-fragment batch on every rank: identical work per GPU
     total_reads = batch["total_mapped_reads"]
     pinned = api.pinned_batch(batch)
     q = api.Quantifier(device=local_rank)
@@ -272,7 +272,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "configs[1]: synthetic 10M-fragment paired-end human-shaped loci (20000 loci), quantification only; one such batch per GPU",
-                       "generator": synth.GENERATOR_VERSION, "seed": "2+rank", "loci_per_gpu": st["n_loci"], "rows_per_gpu": st["n_row"],
+                       "generator": synth.GENERATOR_VERSION, "seed": 2, "loci_per_gpu": st["n_loci"], "rows_per_gpu": st["n_row"],
                        "isoforms_per_gpu": st["n_iso"], "nnz_per_gpu": st["nnz"], "fragments_per_gpu": int(batch["count"].sum()),
                        "em_iters_total_per_gpu": st["em_iters_total"], "max_iter": 1000, "theta_tol": 1e-2,
                        "tiers": {"warp": st["loci_warp"], "cluster": st["loci_cta"], "grid": st["loci_grid"]},
