@@ -209,3 +209,28 @@ def test_config5_shape_with_low_fraction_filter(oracle_mod):
     scale = np.maximum(np.abs(ora["theta"]), 1e-9 * np.repeat(np.add.reduceat(sub["count"].astype(np.float64), sub["loc_row_off"][:-1]), np.diff(sub["loc_iso_off"])))
     assert (np.abs(res["theta"][isos] - ora["theta"]) / np.maximum(scale, 1e-300)).max() < 1e-6
     assert np.array_equal(res["keep"][isos] != 0, ora["keep"] != 0)
+
+
+def test_grid_tier_dense_rows_take_the_oversize_chunk_path(q, oracle_mod):
+    """Rows of ~600 non-zeros: every 32-row chunk exceeds the TMA stage capacity, so the grid kernel's consumers read
+    those chunks straight from global memory while the ring is bypassed."""
+    rng = np.random.default_rng(8)
+    T, R = 900, 2200
+    rows, rp = [], [0]
+    for i in range(R):
+        k = int(rng.integers(450, 750))
+        rows.append(np.sort(rng.choice(T, k, replace=False)))
+        rp.append(rp[-1] + k)
+    col = np.concatenate(rows).astype(np.int32)
+    b = dict(loc_row_off=np.array([0, R], np.int64), loc_iso_off=np.array([0, T], np.int64), row_ptr=np.array(rp, np.int64), col=col,
+             alpha=10.0 ** rng.uniform(-4, -1.5, len(col)), count=rng.integers(0, 50, R).astype(np.int32),
+             iso_len=rng.integers(400, 8000, T).astype(np.int32), total_mapped_reads=1_000_000)
+    ora = oracle_mod.quantify_batch(b, b["total_mapped_reads"], max_iter=60)
+    from strawberry_b200 import api
+    qq = api.Quantifier(max_iter=60)
+    qq.submit_flat(b)
+    qq.run(b["total_mapped_reads"])
+    res = qq.results()
+    assert qq.stats()["loci_grid"] == 1
+    assert_matches_oracle(res, ora, b, "dense-row giant locus")
+    qq.close()
