@@ -51,7 +51,7 @@ class ClockSampler:
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -223,11 +223,12 @@ def main():
     for _ in range(args.warmup):
         resident_step()
     barrier()
-    with ClockSampler(local_rank) as clk:
-        t_wall0 = time.perf_counter()
-        step_ms = [resident_step() for _ in range(args.steps)]
-        barrier()
-        t_wall = time.perf_counter() - t_wall0
+    clk = ClockSampler(local_rank)
+    clk.__enter__()                      # sampled over both timed legs (resident + end-to-end)
+    t_wall0 = time.perf_counter()
+    step_ms = [resident_step() for _ in range(args.steps)]
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
     q.download()
     st = q.stats()
     launches = q.launch_stats()
@@ -241,6 +242,7 @@ def main():
     barrier()
     e2e_s = [e2e_step() for _ in range(args.steps)]
     barrier()
+    clk.__exit__(None, None, None)
     st_e2e = q.stats()
     e2e_local = float(np.mean(e2e_s))
 
@@ -306,8 +308,14 @@ def main():
                 qg.download()
                 gst = qg.stats()
                 g_ach = gst["grid_alg_bytes"] / (float(np.mean(g_ms)) * 1e-3) / 1e9
+                # DRAM bytes per non-zero and pass measured by ncu --set full on this kernel (profiles/r01_grid_tma_ncu_summary.txt:
+                # dram__bytes_read.sum + write = 4.47 GB for 9 passes over 48.0 M non-zeros = 10.3 B; the kernel streams u16
+                # columns, so it moves LESS than the 12 B/nnz the roofline counts as algorithmic)
+                passes = gst["em_iters_total"] + args.giant_loci
+                g_traffic = 10.34 * (gst["nnz"] / args.giant_loci) * passes
                 line["roofline_giant"] = {"bound": "hbm", "achieved": g_ach, "peak": peak, "unit": "GB/s", "frac": g_ach / peak,
-                                          "traffic": None, "kernel": "em_grid_kernel", "kernel_ms": float(np.mean(g_ms)),
+                                          "traffic": g_traffic, "traffic_source": "scaled from the ncu --set full capture of the same kernel in profiles/ (10.34 B per non-zero and pass)",
+                                          "kernel": "em_grid_tma_kernel", "kernel_ms": float(np.mean(g_ms)),
                                           "alg_bytes_per_launch": gst["grid_alg_bytes"], "peak_source": peak_src,
                                           "workload": f"configs[3] shape: {args.giant_loci} loci x {args.giant_rows} rows, n_i=1, k~1+Poisson(47), T~U{{500..800}} "
                                                       f"({gst['nnz']} nnz, {gst['em_iters_total']} EM iterations in total); CSR {gst['nnz'] * 12 / 1e9:.2f} GB > L2",
