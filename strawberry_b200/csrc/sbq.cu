@@ -81,7 +81,7 @@ struct DevBuf {
 };
 
 struct LaunchClass {      // one kernel launch of the cluster tier
-   int cs, lpr;
+   int cs, lpr;           // lpr doubles as the thread count of the launch (CL_NT or CL_NT_SMALL)
    std::vector<int32_t> loci;
    int max_iso = 0;
    size_t max_slice = 0;  // estimated bytes of the largest per-CTA resident CSR slice
@@ -249,12 +249,16 @@ int ensure_origin(sbq_ctx* c) {
    return SBQ_SUCCESS;
 }
 
-size_t cluster_class_smem(int max_iso, size_t slice_bytes) {
+size_t cluster_class_smem(int max_iso, size_t slice_bytes, int nt) {
    // fixed arrays + the larger of (estimated largest resident slice, a full set of streaming accumulators)
    const size_t fixed = cluster_fixed_doubles(max_iso) * sizeof(double);
-   const size_t stream = (size_t)(CL_NT / CL_LPR_STREAM) * max_iso * sizeof(double);
+   const size_t stream = (size_t)(nt / CL_LPR_STREAM) * max_iso * sizeof(double);
    return std::min(fixed + std::max(slice_bytes, stream) + 256, SMEM_CAP);
 }
+
+// single-CTA loci are bucketed by shared-memory need so that small ones do not reserve the footprint of the largest:
+// bucket 0 (<= 24 KB, 128 threads), 1 (<= 56 KB), 2 (<= 112 KB), 3 (rest)
+int smem_bucket(size_t bytes) { return bytes <= 24 * 1024 ? 0 : bytes <= 56 * 1024 ? 1 : bytes <= 112 * 1024 ? 2 : 3; }
 
 int cluster_size_for(int64_t nnz) {
    // ~14 B of shared memory per non-zero (CSR + CSC index): keep a CTA's slice under ~10k non-zeros
@@ -278,9 +282,9 @@ int plan(sbq_ctx* c) {
    c->grid_max_iso = 1;
    c->grid_tma_ok = true;
    std::vector<int64_t> nnz_of(c->n_loci);
-   LaunchClass* slot[5] = {};
+   LaunchClass* slot[5][4] = {};
    std::vector<LaunchClass> tmp;
-   tmp.reserve(5);
+   tmp.reserve(20);
    const int64_t grid_min_nnz = 300 * 1000;   // above this a locus is faster on the whole GPU than on a 16-CTA cluster
    for (int64_t l = 0; l < c->n_loci; ++l) {
       const int64_t R = lro[l + 1] - lro[l], T = lio[l + 1] - lio[l];
@@ -305,15 +309,17 @@ int plan(sbq_ctx* c) {
       } else {
          int cs = c->force_cluster ? c->force_cluster : cluster_size_for(nnz);
          int csi = cs == 1 ? 0 : cs == 2 ? 1 : cs == 4 ? 2 : cs == 8 ? 3 : 4;
-         if (!slot[csi]) {
-            tmp.push_back(LaunchClass{cs, 0, {}, 0, 0, 0, 0});
-            slot[csi] = &tmp.back();
-         }
-         slot[csi]->loci.push_back((int32_t)l);
-         slot[csi]->max_iso = std::max(slot[csi]->max_iso, (int)T);
-         // per-CTA resident slice with 15 % slack for the row-granular split
+         // per-CTA resident slice with 12 % slack for the row-granular split
          const size_t slice = (size_t)(1.12 * (double)cluster_resident_bytes((size_t)(nnz / cs + 1), (size_t)(R / cs + 1), (int)T)) + 512;
-         slot[csi]->max_slice = std::max(slot[csi]->max_slice, slice);
+         const int bucket = cs == 1 ? smem_bucket(cluster_class_smem((int)T, slice, CL_NT_SMALL)) : 3;
+         if (!slot[csi][bucket]) {
+            tmp.push_back(LaunchClass{cs, bucket == 0 ? CL_NT_SMALL : CL_NT, {}, 0, 0, 0, 0});
+            slot[csi][bucket] = &tmp.back();
+         }
+         LaunchClass* lc = slot[csi][bucket];
+         lc->loci.push_back((int32_t)l);
+         lc->max_iso = std::max(lc->max_iso, (int)T);
+         lc->max_slice = std::max(lc->max_slice, slice);
       }
    }
    auto by_size = [&](int32_t a, int32_t b) { return nnz_of[a] != nnz_of[b] ? nnz_of[a] > nnz_of[b] : a < b; };
@@ -321,13 +327,13 @@ int plan(sbq_ctx* c) {
    std::sort(c->grid_list.begin(), c->grid_list.end(), by_size);
    for (auto& lc : tmp) {
       std::sort(lc.loci.begin(), lc.loci.end(), by_size);
-      lc.smem = cluster_class_smem(lc.max_iso, lc.max_slice);
-      if (cluster_stream_groups(lc.max_iso, lc.smem) <= 0)
+      lc.smem = cluster_class_smem(lc.max_iso, lc.max_slice, lc.lpr);
+      if (cluster_stream_groups(lc.max_iso, lc.smem, lc.lpr) <= 0)
          return fail(c, SBQ_ERR_UNSUPPORTED, "locus with %d isoforms does not fit the cluster tier", lc.max_iso);
       c->classes.push_back(std::move(lc));
    }
    // biggest clusters first: they sit on the critical path
-   std::sort(c->classes.begin(), c->classes.end(), [](const LaunchClass& a, const LaunchClass& b) { return a.cs > b.cs; });
+   std::sort(c->classes.begin(), c->classes.end(), [](const LaunchClass& a, const LaunchClass& b) { return a.cs != b.cs ? a.cs > b.cs : a.max_slice > b.max_slice; });
 
    c->h_lists.clear();
    c->warp_list_off = 0;
@@ -353,9 +359,9 @@ int set_kernel_attrs(sbq_ctx* c, K kernel, size_t smem, bool nonportable) {
    return SBQ_SUCCESS;
 }
 
-int launch_cluster_class(sbq_ctx* c, const LaunchClass& lc, cudaStream_t st) {
-   constexpr int NT = CL_NT;
-   auto kernel = em_cluster_kernel<CL_NT>;
+template <int NT>
+int launch_cluster_class_nt(sbq_ctx* c, const LaunchClass& lc, cudaStream_t st) {
+   auto kernel = em_cluster_kernel<NT>;
    int rc = set_kernel_attrs(c, kernel, lc.smem, lc.cs > 8);
    if (rc) return rc;
    cudaLaunchConfig_t cfg{};
@@ -792,7 +798,7 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
       if (!serialize && used_side < N_SIDE_STREAMS) CU(cudaStreamWaitEvent(ss, c->ev_fork, 0));
       LaunchTimer& t = c->lt[2 + used_side % N_SIDE_STREAMS];
       CU(cudaEventRecord(t.e0, ss));
-      int rc = launch_cluster_class(c, lc, ss);
+      int rc = lc.lpr == CL_NT_SMALL ? launch_cluster_class_nt<CL_NT_SMALL>(c, lc, ss) : launch_cluster_class_nt<CL_NT>(c, lc, ss);
       if (rc) return rc;
       CU(cudaEventRecord(t.e1, ss));
       t.used = true;
@@ -848,7 +854,7 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
    for (size_t i = 0; i < c->classes.size(); ++i) {
       LaunchTimer& t = c->lt[2 + i % N_SIDE_STREAMS];
       CU(cudaEventElapsedTime(&ms, t.e0, t.e1));
-      add_stat(2, c->classes[i].cs, 0, c->classes[i].loci, ms);
+      add_stat(2, c->classes[i].cs, c->classes[i].lpr, c->classes[i].loci, ms);
    }
    c->stats.kernel_launches = launches;
    c->solved = true;

@@ -278,16 +278,17 @@ em_warp_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, int ma
 // row pass -> fixed-order sum over groups -> partial theta' exchanged through distributed shared
 // memory (one cluster barrier, double-buffered) -> every CTA forms the same theta' and norm.
 // --------------------------------------------------------------------------------------------
-constexpr int CL_NT = 512;           // threads per CTA of the cluster tier
+constexpr int CL_NT = 512;           // threads per CTA of the cluster tier (small single-CTA loci use CL_NT_SMALL)
+constexpr int CL_NT_SMALL = 128;
 constexpr int CL_LPR_STREAM = 32;    // lanes per row of the streaming fallback
 
 __host__ __device__ inline size_t cluster_fixed_doubles(int T) { return (size_t)6 * T + 8; }
 
 // groups of the streaming fallback that fit next to the fixed arrays
-__host__ __device__ inline int cluster_stream_groups(int T, size_t smem_bytes) {
+__host__ __device__ inline int cluster_stream_groups(int T, size_t smem_bytes, int nt = CL_NT) {
    const long long budget = (long long)(smem_bytes / sizeof(double)) - (long long)cluster_fixed_doubles(T);
    long long G = budget / (T > 0 ? T : 1);
-   if (G > CL_NT / CL_LPR_STREAM) G = CL_NT / CL_LPR_STREAM;
+   if (G > nt / CL_LPR_STREAM) G = nt / CL_LPR_STREAM;
    return (int)G;   // 0 => does not fit
 }
 // bytes of one CTA's resident slice: CSR part (alpha, col, row pointers, counts, r) and the CSC index (pos, row)
@@ -443,7 +444,7 @@ __device__ __forceinline__ void resident_e_pass(const ResidentSlice& S, const do
 }
 
 // M-step on the resident slice through the CSC index: out_j = scale_j * sum_{k in column j} alpha_k r_row(k).
-// Fixed lane assignment and reduction shape -> deterministic, no accumulators, no atomics. Four index entries per
+// Fixed lane assignment and reduction shape -> deterministic, no accumulators, no atomics. Eight index entries per
 // lane are fetched before they are used so that a CSC index living in global scratch (L2) is latency-tolerant.
 template <int NT>
 __device__ __forceinline__ void resident_col_pass(const ResidentSlice& S, const double* scale, double* out, int lpc) {
@@ -454,12 +455,12 @@ __device__ __forceinline__ void resident_col_pass(const ResidentSlice& S, const 
       double sum = 0.0;
       if (j < S.T) {
          const unsigned x1 = S.cp[j + 1];
-         for (unsigned x = S.cp[j] + lg; x < x1; x += 4 * lpc) {
-            unsigned e[4];
+         for (unsigned x = S.cp[j] + lg; x < x1; x += 8 * lpc) {
+            unsigned e[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) e[u] = (x + u * lpc < x1) ? ent[x + u * lpc] : 0xffffffffu;
+            for (int u = 0; u < 8; ++u) e[u] = (x + u * lpc < x1) ? ent[x + u * lpc] : 0xffffffffu;
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < 8; ++u)
                if (e[u] != 0xffffffffu) sum += S.al[e[u] & 0xffffu] * S.r[e[u] >> 16];
          }
       }
@@ -530,7 +531,7 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
    else S.ent = p.csc + (size_t)k_a;   // CSC index of this slice in global scratch (L2); the CSR part stays in shared memory
    S.nrows = nrows; S.T = T; S.nnz = nnz_c;
    GlobalRows grows{rp + ra, p.alpha + k_a, p.col + k_a, p.neff + r0 + ra, k_a};
-   const int G = resident ? 0 : cluster_stream_groups(T, smem_bytes);
+   const int G = resident ? 0 : cluster_stream_groups(T, smem_bytes, NT);
    double* acc = dyn;                                           // [G][T] (streaming only)
    const int g32 = tid / CL_LPR_STREAM, lg32 = tid % CL_LPR_STREAM;
    double* my_acc = acc + (size_t)(g32 < G ? g32 : 0) * T;
@@ -638,6 +639,13 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
 
    const double tol2 = p.tol * p.tol;
    int status = LOCUS_ITER_CAP, iters = 0;
+#ifdef SBQ_PHASE_TIMING
+   long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define SBQ_TICK(k) { const long long t_ = clock64(); ph[k] += t_ - t_prev; t_prev = t_; }
+   long long t_prev = clock64();
+#else
+#define SBQ_TICK(k)
+#endif
    if (kept_all == 0) {
       status = LOCUS_NO_ROWS;
    } else {
@@ -647,8 +655,11 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
          int zero = 0;
          if (resident) {
             resident_e_pass<NT>(S, th, lpr, zero);
+            SBQ_TICK(0)
             zero = __syncthreads_or(zero);
+            SBQ_TICK(1)
             resident_col_pass<NT>(S, th, pb, lpc);
+            SBQ_TICK(2)
          } else {
             if (g32 < G) cluster_em_pass<CL_LPR_STREAM>(grows, nrows, G, g32, lg32, th, my_acc, zero);
             zero = __syncthreads_or(zero);
@@ -660,6 +671,7 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
          }
          if (tid == 0) pb[T] = (double)zero;
          cluster.sync();
+         SBQ_TICK(3)
          double zf = 0.0;
          for (unsigned r = 0; r < CS; ++r) {
             const double* rpb = CS > 1 ? cluster.map_shared_rank(pb, r) : pb;
@@ -673,7 +685,9 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
             }
             nxt[j] = nj;
          }
+         SBQ_TICK(4)
          __syncthreads();
+         SBQ_TICK(5)
          // every warp forms the same ||theta' - theta||^2 (same order in every warp and every CTA)
          double d2 = 0.0;
          for (int j = lane; j < T; j += 32) { const double diff = nxt[j] - cur[j]; d2 += diff * diff; }
@@ -685,9 +699,16 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
             th[j] = (sj != 0) ? nxt[j] / sj : 0.0;
          }
          { double* t_ = cur; cur = nxt; nxt = t_; }
+         SBQ_TICK(6)
          __syncthreads();
+         SBQ_TICK(7)
       }
    }
+#ifdef SBQ_PHASE_TIMING
+   if (rank == 0 && (tid == 0 || tid == NT - 32))
+      printf("locus %d tid %d iters %d resident %d csc_smem %d lpr %d lpc %d nrows %d nnz %u | E %lld or %lld col %lld csync %lld comb %lld sync %lld upd %lld sync %lld (cycles/iter)\n", l, tid, iters,
+             (int)resident, (int)csc_in_smem, lpr, lpc, nrows, nnz_c, ph[0] / iters, ph[1] / iters, ph[2] / iters, ph[3] / iters, ph[4] / iters, ph[5] / iters, ph[6] / iters, ph[7] / iters);
+#endif
    cluster.sync();   // no CTA may exit while a peer can still read its shared memory
 
    if (rank != 0) return;
