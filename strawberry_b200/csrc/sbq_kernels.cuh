@@ -282,7 +282,7 @@ constexpr int CL_NT = 512;           // threads per CTA of the cluster tier (sma
 constexpr int CL_NT_SMALL = 128;
 constexpr int CL_LPR_STREAM = 32;    // lanes per row of the streaming fallback
 
-__host__ __device__ inline size_t cluster_fixed_doubles(int T) { return (size_t)6 * T + 8; }
+__host__ __device__ inline size_t cluster_fixed_doubles(int T) { return (size_t)6 * T + 64; }   // th, theta x2, s_j, exchange area [2T+64]
 
 // groups of the streaming fallback that fit next to the fixed arrays
 __host__ __device__ inline int cluster_stream_groups(int T, size_t smem_bytes, int nt = CL_NT) {
@@ -291,9 +291,11 @@ __host__ __device__ inline int cluster_stream_groups(int T, size_t smem_bytes, i
    if (G > nt / CL_LPR_STREAM) G = nt / CL_LPR_STREAM;
    return (int)G;   // 0 => does not fit
 }
-// bytes of one CTA's resident slice: CSR part (alpha, col, row pointers, counts, r) and the CSC index (pos, row)
+// bytes of one CTA's resident slice: row part (alpha, col, diagonal offsets, row lengths, counts, r) and the CSC index (pos, row)
+__host__ __device__ inline int cluster_diag_slots(int T) { return (T + 7) & ~3; }   // diagonal offsets, read four at a time
 __host__ __device__ inline size_t cluster_resident_csr_bytes(size_t nnz_c, size_t nrows, int T) {
-   return nnz_c * 8 + nrows * 8 + (nrows + 1) * 4 + nrows * 4 + ((size_t)T + 1) * 4 + nnz_c * 2 + 64;
+   const size_t npos = nnz_c + (size_t)T;   // every diagonal may carry one padding slot (odd stride, see the kernel)
+   return (npos + 1) * 8 + (nrows + 2) * 8 + (size_t)cluster_diag_slots(T) * 4 + nrows * 4 + ((size_t)T + 1) * 4 + nrows * 2 + npos * 2 + 64;
 }
 __host__ __device__ inline size_t cluster_resident_bytes(size_t nnz_c, size_t nrows, int T) {
    return cluster_resident_csr_bytes(nnz_c, nrows, T) + nnz_c * 4 + 4;
@@ -383,18 +385,25 @@ __device__ __forceinline__ void cluster_em_pass(const Rows& rows, int nrows, int
    }
 }
 
-// Resident slice of one CTA: CSR arrays plus a per-CTA transposed (CSC) index, all in shared memory.
+// Resident slice of one CTA in shared memory. Rows are sorted by descending length and stored in jagged-diagonal
+// order: element k of sorted row s lives at jd[k] + s, so that consecutive lanes (consecutive rows) read consecutive
+// addresses - no padding and no bank conflicts for a thread-per-row E-step. A per-CTA transposed (CSC) index
+// lists every column's entries for the M-step.
 struct ResidentSlice {
-   double* al;            // [nnz]   alpha, CSR order
-   double* r;             // [nrows] per-row r_i = n_i / d_i of the current iteration (0 for dropped rows)
-   unsigned* rp;          // [nrows+1]
-   int* ne;               // [nrows]
-   unsigned* cp;          // [T+1]   column pointers into pos/row
-   unsigned short* col;   // [nnz]   CSR order (ascending within a row)
-   unsigned* ent;         // [nnz]   CSC order, rows ascending within a column: CSR position | local row << 16
-                          //         (shared memory, or global scratch when only the CSR part fits)
+   double* al;             // [npos+1]  alpha, jagged-diagonal order; al[npos] = 0 (padding target of the M-step)
+   double* r;              // [nrows+1] per sorted row r_s = n_s / d_s of the current iteration (0 for dropped rows); r[nrows] = 0
+   unsigned* jd;           // [jdn]     diagonal offsets (16-byte aligned, read four at a time)
+   int* ne;                // [nrows]   n_s, or -1 for a dropped row
+   unsigned* cp;           // [T+1]     column pointers into ent
+   unsigned short* rlen;   // [nrows]   row lengths, descending
+   unsigned short* col;    // [npos+1]  column of every entry, jagged-diagonal order; col[npos] = 0
+   unsigned* ent;          // [n_ent_s] CSC order, sorted rows ascending within a column: position in al | sorted row << 16
+   unsigned* ent_g;        //           entries n_ent_s.. of the index live in global scratch (L2) when shared memory is full
+   unsigned n_ent_s;
+   __device__ __forceinline__ unsigned get_ent(unsigned x) const { return x < n_ent_s ? ent[x] : ent_g[x]; }
+   __device__ __forceinline__ void put_ent(unsigned x, unsigned v) const { if (x < n_ent_s) ent[x] = v; else ent_g[x] = v; }
    int nrows, T;
-   unsigned nnz;
+   unsigned nnz, npos;     // entries, and positions of al/col (entries + one padding slot per diagonal at most)
 };
 
 // lanes per row / column: the largest power of two <= 32 that still gives every item its own lane group
@@ -407,49 +416,125 @@ __device__ __forceinline__ int lanes_for(int items, int nt) {
    return l;
 }
 
-// E-step on the resident slice: d_i = sum_k alpha_k th[col_k]  ->  r_i = n_i / d_i   (one division per row)
+// E-step on the resident slice: d_s = sum_k alpha_k th[col_k]  ->  r_s = n_s / d_s   (one division per row).
+// lpr lanes share a row and take its entries in interleaved groups of four.
+// E-step, generic form for slices with more rows than threads, one lane per row: four rows per thread at a time
+// (rows tid, tid + NT, ... are sorted by descending length, so the first of the four is the longest).
+template <int NT>
+__device__ __forceinline__ void resident_e_pass_rows4(const ResidentSlice& S, const double* th, int& zero) {
+   const int tid = threadIdx.x;
+   for (int base = 0; base < S.nrows; base += 4 * NT) {
+      int sv[4], ne[4], len[4];
+      double d[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+         sv[u] = base + u * NT + tid;
+         ne[u] = -1; len[u] = 0; d[u] = 0.0;
+         if (sv[u] < S.nrows) {
+            ne[u] = S.ne[sv[u]];
+            if (ne[u] >= 0) len[u] = S.rlen[sv[u]];
+         }
+      }
+      const int maxlen = max(max(len[0], len[1]), max(len[2], len[3]));
+      for (int k = 0; k < maxlen; k += 4) {
+         const uint4 o = *reinterpret_cast<const uint4*>(S.jd + k);
+         const unsigned ov[4] = {o.x, o.y, o.z, o.w};
+         double a[4][4];
+         int c[4][4];
+         // entries past the end of a row read the padding slot (alpha 0, column 0): plain loads, no divergence
+#pragma unroll
+         for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+               const unsigned pos = k + e < len[u] ? ov[e] + (unsigned)sv[u] : S.npos;
+               a[u][e] = S.al[pos];
+               c[u][e] = (int)S.col[pos];
+            }
+#pragma unroll
+         for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+               const double t = a[u][e] * th[c[u][e]];
+               d[u] += k + e < len[u] ? t : 0.0;
+            }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+         if (sv[u] < S.nrows) {
+            double r = 0.0;
+            if (ne[u] >= 0) {
+               if (d[u] == 0) zero = 1; else r = (double)ne[u] / d[u];
+            }
+            S.r[sv[u]] = r;
+         }
+      }
+   }
+}
+
 template <int NT>
 __device__ __forceinline__ void resident_e_pass(const ResidentSlice& S, const double* th, int lpr, int& zero) {
    const int tid = threadIdx.x, g = tid / lpr, lg = tid % lpr, par = NT / lpr;
    for (int base = 0; base < S.nrows; base += par) {
-      const int i = base + g;
-      int ne = -1;
-      unsigned k0 = 0, k1 = 0;
-      if (i < S.nrows) {
-         ne = S.ne[i];
-         if (ne >= 0) { k0 = S.rp[i]; k1 = S.rp[i + 1]; }
+      const int s = base + g;
+      int ne = -1, len = 0;
+      if (s < S.nrows) {
+         ne = S.ne[s];
+         if (ne >= 0) len = S.rlen[s];
       }
-      double d = 0.0;
-      for (unsigned k = k0 + lg; k < k1; k += 4 * lpr) {   // four independent gathers in flight per lane
-         double a[4];
-         int c[4];
-#pragma unroll
-         for (int u = 0; u < 4; ++u) {
-            const bool v = k + u * lpr < k1;
-            a[u] = v ? S.al[k + u * lpr] : 0.0;
-            c[u] = v ? S.col[k + u * lpr] : 0;
-         }
-#pragma unroll
-         for (int u = 0; u < 4; ++u) d += a[u] * th[c[u]];
+      double d0 = 0.0, d1 = 0.0;
+      int k = 4 * lg;
+      // eight entries per trip while two full groups of four remain (sixteen loads in flight per lane)
+      for (; k + 4 * lpr + 4 <= len; k += 8 * lpr) {
+         const uint4 o = *reinterpret_cast<const uint4*>(S.jd + k);
+         const uint4 q = *reinterpret_cast<const uint4*>(S.jd + k + 4 * lpr);
+         const unsigned p0 = o.x + s, p1 = o.y + s, p2 = o.z + s, p3 = o.w + s;
+         const unsigned p4 = q.x + s, p5 = q.y + s, p6 = q.z + s, p7 = q.w + s;
+         const int c0 = S.col[p0], c1 = S.col[p1], c2 = S.col[p2], c3 = S.col[p3];
+         const int c4 = S.col[p4], c5 = S.col[p5], c6 = S.col[p6], c7 = S.col[p7];
+         const double a0 = S.al[p0], a1 = S.al[p1], a2 = S.al[p2], a3 = S.al[p3];
+         const double a4 = S.al[p4], a5 = S.al[p5], a6 = S.al[p6], a7 = S.al[p7];
+         const double t0 = th[c0], t1 = th[c1], t2 = th[c2], t3 = th[c3];
+         const double t4 = th[c4], t5 = th[c5], t6 = th[c6], t7 = th[c7];
+         d0 += a0 * t0;
+         d1 += a1 * t1;
+         d0 += a2 * t2;
+         d1 += a3 * t3;
+         d0 += a4 * t4;
+         d1 += a5 * t5;
+         d0 += a6 * t6;
+         d1 += a7 * t7;
       }
+      for (; k < len; k += 4 * lpr) {                  // last groups: entries past the end read the padding slot
+         const uint4 o = *reinterpret_cast<const uint4*>(S.jd + k);
+         const bool v1 = k + 1 < len, v2 = k + 2 < len, v3 = k + 3 < len;
+         const unsigned p0 = o.x + s, p1 = v1 ? o.y + s : S.npos, p2 = v2 ? o.z + s : S.npos, p3 = v3 ? o.w + s : S.npos;
+         const double a0 = S.al[p0], a1 = S.al[p1], a2 = S.al[p2], a3 = S.al[p3];
+         const int c0 = S.col[p0], c1 = S.col[p1], c2 = S.col[p2], c3 = S.col[p3];
+         const double t0 = a0 * th[c0], t1 = a1 * th[c1], t2 = a2 * th[c2], t3 = a3 * th[c3];
+         d0 += t0;
+         d1 += v1 ? t1 : 0.0;
+         d0 += v2 ? t2 : 0.0;
+         d1 += v3 ? t3 : 0.0;
+      }
+      double d = d0 + d1;
       for (int o = lpr >> 1; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-      if (i < S.nrows && lg == 0) {
+      if (s < S.nrows && lg == 0) {
          double r = 0.0;
          if (ne >= 0) {
             if (d == 0) zero = 1; else r = (double)ne / d;
          }
-         S.r[i] = r;
+         S.r[s] = r;
       }
    }
 }
 
 // M-step on the resident slice through the CSC index: out_j = scale_j * sum_{k in column j} alpha_k r_row(k).
-// Fixed lane assignment and reduction shape -> deterministic, no accumulators, no atomics. Eight index entries per
-// lane are fetched before they are used so that a CSC index living in global scratch (L2) is latency-tolerant.
-template <int NT>
-__device__ __forceinline__ void resident_col_pass(const ResidentSlice& S, const double* scale, double* out, int lpc) {
+// Fixed lane assignment and reduction shape -> deterministic, no accumulators, no atomics.
+// Generic form (any T): lpc lanes per column, index entries read from memory.
+template <int NT, typename Emit>
+__device__ __forceinline__ void resident_col_pass(const ResidentSlice& S, const double* scale, const Emit& emit, int lpc) {
    const int tid = threadIdx.x, g = tid / lpc, lg = tid % lpc, par = NT / lpc;
-   const unsigned* __restrict__ ent = S.ent;
+   const unsigned pad = ((unsigned)S.nrows << 16) | S.npos;
    for (int base = 0; base < S.T; base += par) {
       const int j = base + g;
       double sum = 0.0;
@@ -458,18 +543,198 @@ __device__ __forceinline__ void resident_col_pass(const ResidentSlice& S, const 
          for (unsigned x = S.cp[j] + lg; x < x1; x += 8 * lpc) {
             unsigned e[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) e[u] = (x + u * lpc < x1) ? ent[x + u * lpc] : 0xffffffffu;
+            for (int u = 0; u < 8; ++u) e[u] = (x + u * lpc < x1) ? S.get_ent(x + u * lpc) : pad;
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-               if (e[u] != 0xffffffffu) sum += S.al[e[u] & 0xffffu] * S.r[e[u] >> 16];
+            for (int u = 0; u < 8; ++u) sum += S.al[e[u] & 0xffffu] * S.r[e[u] >> 16];
          }
       }
       for (int o = lpc >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      if (j < S.T && lg == 0) out[j] = scale ? scale[j] * sum : sum;
+      if (j < S.T && lg == 0) *emit.ptr(j) = scale ? scale[j] * sum : sum;
    }
 }
 
+// Balanced form (items <= threads): every thread owns one (item, lane) slot for the whole solve. Rows and columns get
+// a power-of-two number of lanes in proportion to their length, so that every lane walks about the same number of
+// entries. With NCACHE > 0 a column lane keeps its first NCACHE index entries in registers (for slices whose CSC index
+// does not fit shared memory and would otherwise be re-read from L2 every iteration).
+template <int NCACHE>
+struct ColSlot {
+   int j;                      // column, or -1 for an idle thread
+   int q, lanes, wl;           // this thread is lane q of `lanes`; wl = largest group of the warp
+   unsigned x_tail, x1;        // index entries beyond the cached ones: x_tail, x_tail + lanes, ... < x1
+   int ncache;                 // cached entries that are real (the rest point at the zero padding)
+   double* out;                // where lane 0 of the column stores the result
+   unsigned e[NCACHE > 0 ? NCACHE : 1];
+};
+struct RowSlot {
+   int s;                      // sorted row, or -1 for an idle thread
+   int q, lanes, wl;           // this thread is lane q of `lanes`; wl = largest group of the warp
+   int len;                    // entries of the row (0 for a dropped row)
+   int ne;                     // n_s, or -1 for a dropped row
+};
+
+// Slots for n_items <= NT items of the given lengths: lanes_i = ceil(len_i / E) (1..32) with E the smallest target
+// (in steps of 1/8) for which all lanes fit the CTA; the lanes of an item are consecutive threads of one warp.
+// Returns this thread's slot: item | lane << 16 | lanes << 24, or 0xffffffff for an idle thread.
 template <int NT>
+__device__ __forceinline__ unsigned assign_slots(int n_items, int my_len, unsigned total_work, unsigned* s_slot, int* s_lanes, int* s_total) {
+   const int tid = threadIdx.x;
+   // sum_i ceil(len_i / E) ~ total / E + n_items / 2, and a little is lost at warp boundaries
+   const int budget = max(NT / 4, NT - n_items / 2 - 16);
+   int E = max(1, (int)((total_work + budget - 1) / budget));
+   for (;;) {
+      if (tid < n_items) s_lanes[tid] = min(32, max(1, (my_len + E - 1) / E));
+      __syncthreads();
+      if (tid == 0) {                         // greedy packing in item order; a group never straddles a warp
+         int off = 0;
+         for (int i0 = 0; i0 < n_items; i0 += 8) {
+            int L[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) L[u] = i0 + u < n_items ? s_lanes[i0 + u] : 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+               if ((off & 31) + L[u] > 32) off = (off + 31) & ~31;
+               const int o = off;
+               off += L[u];
+               L[u] = o | (L[u] << 16);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+               if (i0 + u < n_items) s_lanes[i0 + u] = L[u];
+         }
+         *s_total = off;
+      }
+      __syncthreads();
+      const int total = *s_total;
+      if (total <= NT) break;
+      __syncthreads();
+      E += max(1, E >> 3);
+   }
+   s_slot[tid] = 0xffffffffu;
+   __syncthreads();
+   if (tid < n_items) {
+      const int off = s_lanes[tid] & 0xffff, L = s_lanes[tid] >> 16;
+      for (int q = 0; q < L; ++q) s_slot[off + q] = (unsigned)tid | ((unsigned)q << 16) | ((unsigned)L << 24);
+   }
+   __syncthreads();
+   const unsigned sl = s_slot[tid];
+   __syncthreads();
+   return sl;
+}
+
+// fixed-shape sum over the lanes of a slot group (consecutive lanes of one warp); lane 0 of the group holds the result.
+// wl = the largest group of this warp (warp-uniform), so warps of single-lane groups do not shuffle at all
+__device__ __forceinline__ double group_sum(double v, int q, int lanes, int wl) {
+   for (int o = 1; o < wl; o <<= 1) {
+      const double u = __shfl_down_sync(0xffffffffu, v, o);
+      if (q + o < lanes) v += u;
+   }
+   return v;
+}
+
+// E-step, balanced form: the lanes of a row take its entries in interleaved groups of four.
+__device__ __forceinline__ void slot_e_pass(const ResidentSlice& S, const RowSlot& rs, const double* th, int& zero) {
+   const unsigned s = (unsigned)max(rs.s, 0);
+   const int len = rs.len, step = 4 * rs.lanes;
+   double d0 = 0.0, d1 = 0.0;
+   int k = 4 * rs.q;
+   // eight entries per trip while two full groups of four remain (sixteen loads in flight per lane)
+   for (; k + step + 4 <= len; k += 2 * step) {
+      const uint4 o = *reinterpret_cast<const uint4*>(S.jd + k);
+      const uint4 q = *reinterpret_cast<const uint4*>(S.jd + k + step);
+      const unsigned p0 = o.x + s, p1 = o.y + s, p2 = o.z + s, p3 = o.w + s;
+      const unsigned p4 = q.x + s, p5 = q.y + s, p6 = q.z + s, p7 = q.w + s;
+      const int c0 = S.col[p0], c1 = S.col[p1], c2 = S.col[p2], c3 = S.col[p3];
+      const int c4 = S.col[p4], c5 = S.col[p5], c6 = S.col[p6], c7 = S.col[p7];
+      const double a0 = S.al[p0], a1 = S.al[p1], a2 = S.al[p2], a3 = S.al[p3];
+      const double a4 = S.al[p4], a5 = S.al[p5], a6 = S.al[p6], a7 = S.al[p7];
+      const double t0 = th[c0], t1 = th[c1], t2 = th[c2], t3 = th[c3];
+      const double t4 = th[c4], t5 = th[c5], t6 = th[c6], t7 = th[c7];
+      d0 += a0 * t0;
+      d1 += a1 * t1;
+      d0 += a2 * t2;
+      d1 += a3 * t3;
+      d0 += a4 * t4;
+      d1 += a5 * t5;
+      d0 += a6 * t6;
+      d1 += a7 * t7;
+   }
+   for (; k < len; k += step) {                       // last groups: entries past the end read the padding slot
+      const uint4 o = *reinterpret_cast<const uint4*>(S.jd + k);
+      const bool v1 = k + 1 < len, v2 = k + 2 < len, v3 = k + 3 < len;
+      const unsigned p0 = o.x + s, p1 = v1 ? o.y + s : S.npos, p2 = v2 ? o.z + s : S.npos, p3 = v3 ? o.w + s : S.npos;
+      const double a0 = S.al[p0], a1 = S.al[p1], a2 = S.al[p2], a3 = S.al[p3];
+      const int c0 = S.col[p0], c1 = S.col[p1], c2 = S.col[p2], c3 = S.col[p3];
+      const double t0 = a0 * th[c0], t1 = a1 * th[c1], t2 = a2 * th[c2], t3 = a3 * th[c3];
+      d0 += t0;
+      d1 += v1 ? t1 : 0.0;
+      d0 += v2 ? t2 : 0.0;
+      d1 += v3 ? t3 : 0.0;
+   }
+   const double d = group_sum(d0 + d1, rs.q, rs.lanes, rs.wl);
+   if (rs.s >= 0 && rs.q == 0) {
+      double r = 0.0;
+      if (rs.ne >= 0) {
+         if (d == 0) zero = 1; else r = (double)rs.ne / d;
+      }
+      S.r[s] = r;
+   }
+}
+
+template <int NCACHE>
+__device__ __forceinline__ void slot_col_pass(const ResidentSlice& S, const ColSlot<NCACHE>& cs, const double* scale) {
+   double s0 = 0.0, s1 = 0.0;
+   if (NCACHE > 0) {
+#pragma unroll
+      for (int u0 = 0; u0 < NCACHE; u0 += 8) {
+         if (u0 < cs.ncache) {
+#pragma unroll
+            for (int u = u0; u < u0 + 8; u += 2) {
+               s0 += S.al[cs.e[u] & 0xffffu] * S.r[cs.e[u] >> 16];
+               s1 += S.al[cs.e[u + 1] & 0xffffu] * S.r[cs.e[u + 1] >> 16];
+            }
+         }
+      }
+   }
+   if (cs.x_tail < cs.x1) {                                   // the (rest of the) index comes from memory
+      const unsigned pad = ((unsigned)S.nrows << 16) | S.npos;
+      for (unsigned x = cs.x_tail; x < cs.x1; x += 8 * cs.lanes) {
+         unsigned e[8];
+#pragma unroll
+         for (int u = 0; u < 8; ++u) e[u] = (x + u * cs.lanes < cs.x1) ? S.get_ent(x + u * cs.lanes) : pad;
+         double a[8], r[8];
+#pragma unroll
+         for (int u = 0; u < 8; ++u) { a[u] = S.al[e[u] & 0xffffu]; r[u] = S.r[e[u] >> 16]; }
+#pragma unroll
+         for (int u = 0; u < 8; u += 2) {
+            s0 += a[u] * r[u];
+            s1 += a[u + 1] * r[u + 1];
+         }
+      }
+   }
+   const double sum = group_sum(s0 + s1, cs.q, cs.lanes, cs.wl);
+   if (cs.j >= 0 && cs.q == 0) *cs.out = scale ? scale[cs.j] * sum : sum;
+}
+
+// Where the partial theta'_j of this CTA goes: column j is owned by CTA j / B of the cluster, which keeps one
+// row of B partials per peer in its exchange area (written through distributed shared memory).
+struct OwnerMap {
+   cg::cluster_group* cluster;
+   double* stage;     // [CS][B] in every CTA
+   int B;
+   unsigned rank, CS;
+   __device__ __forceinline__ double* ptr(int j) const {
+      const int o = j / B;
+      double* base = CS > 1 ? cluster->map_shared_rank(stage, (unsigned)o) : stage;
+      return base + (size_t)rank * B + (j - o * B);
+   }
+};
+struct LocalOut {
+   double* out;
+   __device__ __forceinline__ double* ptr(int j) const { return out + j; }
+};
+
+template <int NT, int NCACHE>
 __global__ void __launch_bounds__(NT)
 em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, unsigned smem_bytes) {
    cg::cluster_group cluster = cg::this_cluster();
@@ -489,8 +754,8 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
    double* bufA = th + T;              // [T] theta (current / next, swapped by pointer)
    double* bufB = bufA + T;            // [T]
    double* sdiv = bufB + T;            // [T] column sums s_j of the kept rows
-   double* part = sdiv + T;            // [2][T+4] exchange buffers: partial theta', flag, total, kept
-   double* dyn = part + 2 * (T + 4);   // resident slice, or the streaming accumulators
+   double* part = sdiv + T;            // [2T+64] exchange area: stage [CS][B] of partial theta', dsq [B], flags [16], d2p [16]
+   double* dyn = part + 2 * T + 64;    // resident slice, or the streaming accumulators
    __shared__ double red[NT / 32];
    __shared__ int s_rows[2];
    double* cur = bufA;
@@ -517,54 +782,181 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
    const unsigned nnz_c = (unsigned)(rp[rb] - k_a);
 
    const size_t used = (size_t)((char*)dyn - (char*)smem);
-   const bool small_idx = nnz_c <= 65535u && nrows <= 65535;
+   const int lpr = lanes_for(nrows, NT), lpc = lanes_for(T, NT);
+   // longest row of the slice: the diagonal table has room for rows of up to T entries (a valid row has no more)
+   int too_long = 0;
+   for (int i = tid; i < nrows; i += NT) too_long |= (rp[ra + i + 1] - rp[ra + i]) > (int64_t)T;
+   too_long = __syncthreads_or(too_long);
+   const bool small_idx = (uint64_t)nnz_c + (uint64_t)T <= 65535u && nrows <= 65535 && !too_long;
+   const unsigned npos = nnz_c + (unsigned)T;
    const bool csc_in_smem = small_idx && used + cluster_resident_bytes(nnz_c, (size_t)nrows, T) <= smem_bytes;
    const bool resident = small_idx && used + cluster_resident_csr_bytes(nnz_c, (size_t)nrows, T) <= smem_bytes;
+   const int jdn = cluster_diag_slots(T);
    ResidentSlice S;
    S.al = dyn;
-   S.r = S.al + nnz_c;
-   S.rp = (unsigned*)(S.r + nrows);
-   S.ne = (int*)(S.rp + nrows + 1);
+   S.r = S.al + npos + 1;
+   S.jd = (unsigned*)(S.r + nrows + 1 + ((npos + nrows) & 1u));                             // 16-byte aligned
+   S.ne = (int*)(S.jd + jdn);
    S.cp = (unsigned*)(S.ne + nrows);
-   S.col = (unsigned short*)(S.cp + T + 1);
-   if (csc_in_smem) S.ent = (unsigned*)(S.col + nnz_c + (nnz_c & 1u));                       // 4-byte aligned
-   else S.ent = p.csc + (size_t)k_a;   // CSC index of this slice in global scratch (L2); the CSR part stays in shared memory
-   S.nrows = nrows; S.T = T; S.nnz = nnz_c;
+   S.rlen = (unsigned short*)(S.cp + T + 1);
+   S.col = S.rlen + nrows;
+   S.ent = (unsigned*)(S.col + npos + 1 + ((npos + 1 + nrows) & 1u));                        // 4-byte aligned
+   S.ent_g = p.csc + (size_t)k_a;      // the part of the CSC index that does not fit shared memory lives in global scratch (L2)
+   S.n_ent_s = 0;
+   if (csc_in_smem) S.n_ent_s = nnz_c;
+   else if (resident) S.n_ent_s = (unsigned)min((size_t)nnz_c, (smem_bytes - used - cluster_resident_csr_bytes(nnz_c, (size_t)nrows, T)) / 4);
+   S.nrows = nrows; S.T = T; S.nnz = nnz_c; S.npos = npos;
    GlobalRows grows{rp + ra, p.alpha + k_a, p.col + k_a, p.neff + r0 + ra, k_a};
    const int G = resident ? 0 : cluster_stream_groups(T, smem_bytes, NT);
    double* acc = dyn;                                           // [G][T] (streaming only)
    const int g32 = tid / CL_LPR_STREAM, lg32 = tid % CL_LPR_STREAM;
    double* my_acc = acc + (size_t)(g32 < G ? g32 : 0) * T;
-   const int lpr = lanes_for(nrows, NT), lpc = lanes_for(T, NT);
+   const bool use_slots = resident && T <= NT;            // balanced M-step
+   const bool use_row_slots = resident && nrows <= NT;    // balanced E-step
+   ColSlot<NCACHE> slot;
+   slot.j = -1; slot.q = 0; slot.lanes = 1; slot.wl = 1; slot.x_tail = slot.x1 = 0; slot.ncache = 0; slot.out = part;
+   RowSlot rslot;
+   rslot.s = -1; rslot.q = 0; rslot.lanes = 1; rslot.wl = 1; rslot.len = 0; rslot.ne = -1;
 
+#ifdef SBQ_PHASE_TIMING
+   long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define SBQ_TICK(k) { const long long t_ = clock64(); ph[k] += t_ - t_prev; t_prev = t_; }
+#define SBQ_STICK(k) { const long long t_ = clock64(); st[k] += t_ - t_prev; t_prev = t_; }
+   long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+   long long t_prev = clock64();
+   const long long t_start = t_prev;
+#else
+#define SBQ_TICK(k)
+#define SBQ_STICK(k)
+#endif
    long long tot = 0;
    int kept = 0;
    if (resident) {
-      // ---- load the slice, row filter, CSC index
-      const int32_t* __restrict__ cnt = p.count + r0 + ra;
-      for (unsigned k = tid; k < nnz_c; k += NT) { S.al[k] = grows.al[k]; S.col[k] = (unsigned short)grows.col[k]; }
-      for (int i = tid; i <= nrows; i += NT) S.rp[i] = (unsigned)(rp[ra + i] - k_a);
-      for (int j = tid; j <= T; j += NT) S.cp[j] = 0;
+      // ---- rows sorted by descending length (ties by row index): bitonic sort of (65535 - len) << 16 | row
+      unsigned* keys = (unsigned*)S.al;                                    // scratch: alpha is loaded afterwards
+      int P = 1;
+      while (P < nrows) P <<= 1;
+      for (int i = tid; i < P; i += NT)
+         keys[i] = i < nrows ? ((65535u - (unsigned)(rp[ra + i + 1] - rp[ra + i])) << 16) | (unsigned)i : 0xffffffffu;
       __syncthreads();
-      {
-         const int g = tid / lpr, lg = tid % lpr, par = NT / lpr;
-         for (int base = 0; base < nrows; base += par) {
-            const int i = base + g;
-            unsigned k0 = 0, k1 = 0;
-            if (i < nrows) { k0 = S.rp[i]; k1 = S.rp[i + 1]; }
-            int keep = 0;
-            for (unsigned k = k0 + lg; k < k1; k += lpr) keep |= S.al[k] > p.row_eps;
-            for (int o = lpr >> 1; o > 0; o >>= 1) keep |= __shfl_xor_sync(0xffffffffu, keep, o);
-            if (i < nrows && lg == 0) {
-               const int n = cnt[i];
-               S.ne[i] = keep ? n : -1;
-               S.r[i] = keep ? 1.0 : 0.0;
-               tot += n;
-               kept += keep;
+      for (int kk = 2; kk <= P; kk <<= 1) {
+         for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+            for (int i = tid; i < P; i += NT) {
+               const int x = i ^ jj;
+               if (x > i) {
+                  const unsigned a = keys[i], b = keys[x];
+                  if (((i & kk) == 0) ? (a > b) : (a < b)) { keys[i] = b; keys[x] = a; }
+               }
             }
+            __syncthreads();
          }
       }
-      for (unsigned k = tid; k < nnz_c; k += NT) atomicAdd(&S.cp[S.col[k] + 1], 1u);       // column counts (integers: exact)
+      SBQ_STICK(0)
+      for (int i = tid; i < nrows; i += NT) {
+         const unsigned key = keys[i];
+         S.rlen[i] = (unsigned short)(65535u - (key >> 16));
+         S.ne[i] = (int)(key & 0xffffu);                                   // original row, until the fill replaces it by n_s
+      }
+      for (int j = tid; j <= T; j += NT) S.cp[j] = 0;
+      __syncthreads();
+      // ---- diagonal offsets: diagonal k holds the rows longer than k (a prefix of the sorted rows)
+      for (int k = tid; k < jdn; k += NT) {
+         unsigned v = 0;
+         if (k > 0) {
+            int lo = 0, hi = nrows;                                        // first sorted row with rlen <= k - 1
+            while (lo < hi) {
+               const int mid = (lo + hi) >> 1;
+               if ((int)S.rlen[mid] > k - 1) lo = mid + 1; else hi = mid;
+            }
+            v = (unsigned)lo | (lo > 0 ? 1u : 0u);                         // odd stride: neighbouring diagonals fall into different banks
+         }
+         S.jd[k] = v;
+      }
+      __syncthreads();
+      if (tid < 32) {                                                      // inclusive scan over jdn (warp 0)
+         const int chunk = (jdn + 31) / 32, k0 = lane * chunk, k1 = min(jdn, k0 + chunk);
+         unsigned sum = 0;
+         for (int k = k0; k < k1; ++k) sum += S.jd[k];
+         unsigned incl = sum;
+         for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+         }
+         unsigned run = incl - sum;
+         for (int k = k0; k < k1; ++k) { run += S.jd[k]; S.jd[k] = run; }
+      }
+      __syncthreads();
+      SBQ_STICK(1)
+      // ---- load the slice, row filter, column counts: lf lanes per row
+      {
+         const int32_t* __restrict__ cnt = p.count + r0 + ra;
+         int lf = 1;
+         while (lf < 32 && (long long)lf * nrows < (long long)nnz_c) lf <<= 1;      // ~ mean row length
+         const int g = tid / lf, lg = tid % lf, par = NT / lf;
+         // two rows per trip, the first four chunks of each fetched before anything is stored (eight loads in flight)
+         for (int base = 0; base < nrows; base += 2 * par) {
+            int sv[2], iv[2], lenv[2], keepv[2];
+            unsigned g0v[2];
+            double a[2][4];
+            int c[2][4];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+               sv[r] = base + r * par + g;
+               iv[r] = 0; lenv[r] = 0; g0v[r] = 0; keepv[r] = 0;
+               if (sv[r] < nrows) {
+                  iv[r] = S.ne[sv[r]];
+                  lenv[r] = S.rlen[sv[r]];
+               }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+               if (sv[r] < nrows) g0v[r] = (unsigned)(rp[ra + iv[r]] - k_a);
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+               for (int u = 0; u < 4; ++u) {
+                  const int k = lg + u * lf;
+                  a[r][u] = 0.0; c[r][u] = 0;
+                  if (k < lenv[r]) { a[r][u] = grows.al[g0v[r] + k]; c[r][u] = grows.col[g0v[r] + k]; }
+               }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+#pragma unroll
+               for (int u = 0; u < 4; ++u) {
+                  const int k = lg + u * lf;
+                  if (k < lenv[r]) {
+                     const unsigned pos = S.jd[k] + sv[r];
+                     S.al[pos] = a[r][u];
+                     S.col[pos] = (unsigned short)c[r][u];
+                     keepv[r] |= a[r][u] > p.row_eps;
+                     atomicAdd(&S.cp[c[r][u] + 1], 1u);                               // column counts (integers: exact)
+                  }
+               }
+               for (int k = lg + 4 * lf; k < lenv[r]; k += lf) {
+                  const double av = grows.al[g0v[r] + k];
+                  const int cv = grows.col[g0v[r] + k];
+                  const unsigned pos = S.jd[k] + sv[r];
+                  S.al[pos] = av;
+                  S.col[pos] = (unsigned short)cv;
+                  keepv[r] |= av > p.row_eps;
+                  atomicAdd(&S.cp[cv + 1], 1u);
+               }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+               int keep = keepv[r];
+               for (int o = lf >> 1; o > 0; o >>= 1) keep |= __shfl_xor_sync(0xffffffffu, keep, o);
+               if (sv[r] < nrows && lg == 0) {
+                  const int n = cnt[iv[r]];
+                  S.ne[sv[r]] = keep ? n : -1;
+                  S.r[sv[r]] = keep ? 1.0 : 0.0;
+                  tot += n;
+                  kept += keep;
+               }
+            }
+         }
+         if (tid == 0) { S.al[npos] = 0.0; S.col[npos] = 0; S.r[nrows] = 0.0; }
+      }
       __syncthreads();
       if (tid < 32) {                                                                        // exclusive scan over T (warp 0)
          const int chunk = (T + 31) / 32, j0 = lane * chunk, j1 = min(T, j0 + chunk);
@@ -579,29 +971,99 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
          for (int j = j0; j < j1; ++j) { const unsigned c = S.cp[j + 1]; S.cp[j + 1] = run + c; run += c; }
       }
       __syncthreads();
-      // ordered fill, one warp per column: rows are visited in order and a row holds column j at most once
-      // (binary search, columns ascend within a row), so every column lists its entries by ascending row.
-      for (int j = tid >> 5; j < T; j += NT / 32) {
-         unsigned w = S.cp[j];
-         const unsigned w_end = S.cp[j + 1];
-         for (int base = 0; base < nrows && w < w_end; base += 32) {
-            const int i = base + lane;
-            unsigned found = 0xffffffffu;
-            if (i < nrows) {
-               unsigned lo = S.rp[i], hi = S.rp[i + 1];
-               while (lo < hi) {
-                  const unsigned mid = (lo + hi) >> 1;
-                  if (S.col[mid] < (unsigned)j) lo = mid + 1; else hi = mid;
+      SBQ_STICK(2)
+      // ordered fill: a warp owns a chunk of up to 32 neighbouring columns (lane i keeps the write pointer of column
+      // jlo + i) and walks the sorted rows 32 at a time, every lane with a cursor into its own row (columns ascend
+      // within a row). Every column lists its entries by ascending sorted row; no atomics, fixed order.
+      {
+         const int nw = NT / 32, w = tid >> 5;
+         const int C = min(32, (T + nw - 1) / nw);
+         const int nchunks = (T + C - 1) / C;
+         const unsigned lt = (1u << lane) - 1u;
+         for (int ch = w; ch < nchunks; ch += nw) {
+            const int jlo = ch * C, jn = min(C, T - jlo);
+            unsigned wp = lane < jn ? S.cp[jlo + lane] : 0u;
+            for (int base = 0; base < nrows; base += 32) {
+               const int s = base + lane;
+               int len = 0, cur = 0;
+               if (s < nrows) {
+                  len = S.rlen[s];
+                  int lo = 0, hi = len;                       // first entry of the row with column >= jlo
+                  while (lo < hi) {
+                     const int mid = (lo + hi) >> 1;
+                     if ((int)S.col[S.jd[mid] + s] < jlo) lo = mid + 1; else hi = mid;
+                  }
+                  cur = lo;
                }
-               if (lo < S.rp[i + 1] && S.col[lo] == (unsigned)j) found = lo;
+               unsigned pos = 0;
+               int nextc = -1;
+               if (cur < len) { pos = S.jd[cur] + s; nextc = S.col[pos]; }
+               if (__ballot_sync(0xffffffffu, nextc >= 0 && nextc < jlo + jn) == 0u) continue;
+               for (int jj = 0; jj < jn; ++jj) {
+                  const bool hit = nextc == jlo + jj;
+                  const unsigned m = __ballot_sync(0xffffffffu, hit);
+                  const unsigned basep = __shfl_sync(0xffffffffu, wp, jj);
+                  if (hit) {
+                     S.put_ent(basep + __popc(m & lt), pos | ((unsigned)s << 16));
+                     ++cur;
+                     nextc = -1;
+                     if (cur < len) { pos = S.jd[cur] + s; nextc = S.col[pos]; }
+                  }
+                  if (lane == jj) wp += __popc(m);
+               }
             }
-            const unsigned m = __ballot_sync(0xffffffffu, found != 0xffffffffu);
-            if (found != 0xffffffffu) S.ent[w + __popc(m & ((1u << lane) - 1u))] = found | ((unsigned)i << 16);
-            w += __popc(m);
          }
       }
       __syncthreads();
-      resident_col_pass<NT>(S, nullptr, part, lpc);                                         // s_j partial (r = keep flag)
+      SBQ_STICK(3)
+      // ---- balanced slots (rows for the E-step, columns for the M-step)
+      __shared__ unsigned s_slot[NT];
+      __shared__ int s_lanes[NT];
+      __shared__ int s_total;
+      if (use_row_slots) {
+         const int len_s = tid < nrows ? (int)S.rlen[tid] : 0;
+         const unsigned sl = assign_slots<NT>(nrows, len_s, nnz_c, s_slot, s_lanes, &s_total);
+         if (sl != 0xffffffffu) {
+            rslot.s = (int)(sl & 0xffffu);
+            rslot.q = (int)((sl >> 16) & 0xffu);
+            rslot.lanes = (int)(sl >> 24);
+            rslot.ne = S.ne[rslot.s];
+            rslot.len = rslot.ne >= 0 ? (int)S.rlen[rslot.s] : 0;
+         }
+         rslot.wl = __reduce_max_sync(0xffffffffu, rslot.lanes);
+      }
+      SBQ_STICK(4)
+      if (use_slots) {
+         const int len_j = tid < T ? (int)(S.cp[tid + 1] - S.cp[tid]) : 0;
+         const unsigned sl = assign_slots<NT>(T, len_j, nnz_c, s_slot, s_lanes, &s_total);
+         const unsigned pad = ((unsigned)nrows << 16) | npos;
+         if (sl != 0xffffffffu) {
+            slot.j = (int)(sl & 0xffffu);
+            slot.lanes = (int)(sl >> 24);
+            slot.q = (int)((sl >> 16) & 0xffu);
+            const unsigned x0 = S.cp[slot.j] + (unsigned)slot.q;
+            slot.x1 = S.cp[slot.j + 1];
+            slot.x_tail = x0 + (unsigned)NCACHE * slot.lanes;
+            if (NCACHE > 0) {
+#pragma unroll
+               for (int u = 0; u < NCACHE; ++u) {
+                  const unsigned x = x0 + (unsigned)u * slot.lanes;
+                  const bool v = x < slot.x1;
+                  slot.e[u] = v ? S.get_ent(x) : pad;
+                  slot.ncache += v;
+               }
+            }
+            slot.out = part + slot.j;
+         } else if (NCACHE > 0) {
+#pragma unroll
+            for (int u = 0; u < NCACHE; ++u) slot.e[u] = pad;
+         }
+         slot.wl = __reduce_max_sync(0xffffffffu, slot.lanes);
+         SBQ_STICK(5)
+         slot_col_pass(S, slot, nullptr);                                                     // s_j partial (r = keep flag)
+      } else {
+         resident_col_pass<NT>(S, nullptr, LocalOut{part}, lpc);
+      }
    } else {
       for (int x = tid; x < G * T; x += NT) acc[x] = 0.0;
       __syncthreads();
@@ -640,25 +1102,34 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
    const double tol2 = p.tol * p.tol;
    int status = LOCUS_ITER_CAP, iters = 0;
 #ifdef SBQ_PHASE_TIMING
-   long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define SBQ_TICK(k) { const long long t_ = clock64(); ph[k] += t_ - t_prev; t_prev = t_; }
-   long long t_prev = clock64();
-#else
-#define SBQ_TICK(k)
+   const long long t_setup = clock64() - t_start;
+   t_prev = clock64();
 #endif
+   // ---- exchange area: column j belongs to CTA j / B; every CTA pushes its partial theta'_j to the owner, the owner
+   //      adds the CS partials in a fixed shape and pushes theta'_j and theta'_j / s_j back to everyone
+   const int B = (T + (int)CS - 1) / (int)CS;
+   double* stage = part;                       // [CS][B]
+   double* dsq = part + T + 16;                // [B] squared changes of the owned columns
+   double* flags = part + 2 * T + 32;          // [CS] zero-denominator flag of every CTA
+   double* d2p = flags + 16;                   // [CS] partial ||theta' - theta||^2 of every owner
+   const OwnerMap own{&cluster, stage, B, rank, CS};
+   if (slot.j >= 0) slot.out = own.ptr(slot.j);
+   const int nb = max(0, min(B, T - (int)rank * B));      // columns this CTA owns
    if (kept_all == 0) {
       status = LOCUS_NO_ROWS;
    } else {
       for (int it = 0; it < p.max_iter; ++it) {
          iters = it + 1;
-         double* pb = part + (size_t)(it & 1) * (T + 4);
          int zero = 0;
          if (resident) {
-            resident_e_pass<NT>(S, th, lpr, zero);
+            if (use_row_slots) slot_e_pass(S, rslot, th, zero);
+            else if (lpr == 1) resident_e_pass_rows4<NT>(S, th, zero);
+            else resident_e_pass<NT>(S, th, lpr, zero);
             SBQ_TICK(0)
             zero = __syncthreads_or(zero);
             SBQ_TICK(1)
-            resident_col_pass<NT>(S, th, pb, lpc);
+            if (use_slots) slot_col_pass(S, slot, th);
+            else resident_col_pass<NT>(S, th, own, lpc);
             SBQ_TICK(2)
          } else {
             if (g32 < G) cluster_em_pass<CL_LPR_STREAM>(grows, nrows, G, g32, lg32, th, my_acc, zero);
@@ -666,48 +1137,58 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
             for (int j = tid; j < T; j += NT) {
                double sj = 0.0;
                for (int gg = 0; gg < G; ++gg) { sj += acc[(size_t)gg * T + j]; acc[(size_t)gg * T + j] = 0.0; }
-               pb[j] = sj;
+               *own.ptr(j) = sj;
             }
          }
-         if (tid == 0) pb[T] = (double)zero;
-         cluster.sync();
+         if (tid < (int)CS) (CS > 1 ? cluster.map_shared_rank(flags, (unsigned)tid) : flags)[rank] = (double)zero;
+         if (CS > 1) cluster.sync(); else __syncthreads();
          SBQ_TICK(3)
          double zf = 0.0;
-         for (unsigned r = 0; r < CS; ++r) {
-            const double* rpb = CS > 1 ? cluster.map_shared_rank(pb, r) : pb;
-            zf += rpb[T];
-         }
-         for (int j = tid; j < T; j += NT) {
-            double nj = 0.0;
-            for (unsigned r = 0; r < CS; ++r) {
-               const double* rpb = CS > 1 ? cluster.map_shared_rank(pb, r) : pb;
-               nj += rpb[j];
+         for (unsigned r = 0; r < CS; ++r) zf += flags[r];
+         if (zf != 0.0) { status = LOCUS_ZERO_DENOM; break; }
+         // owner: CS lanes per owned column, fixed butterfly; lane r pushes the result to peer r
+         {
+            const int items = nb * (int)CS;
+            const unsigned r = (unsigned)tid % CS;
+            double* peer_nxt = CS > 1 ? cluster.map_shared_rank(nxt, r) : nxt;
+            double* peer_th = CS > 1 ? cluster.map_shared_rank(th, r) : th;
+            for (int base = 0; base < items; base += NT) {
+               const int x = base + tid, jj = x / (int)CS;
+               double v = x < items ? stage[(size_t)r * B + jj] : 0.0;
+               for (unsigned o = CS >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+               if (x < items) {
+                  const int j = (int)rank * B + jj;
+                  const double sj = sdiv[j];
+                  peer_nxt[j] = v;
+                  peer_th[j] = (sj != 0) ? v / sj : 0.0;
+                  if (r == 0) { const double diff = v - cur[j]; dsq[jj] = diff * diff; }
+               }
             }
-            nxt[j] = nj;
          }
          SBQ_TICK(4)
          __syncthreads();
-         SBQ_TICK(5)
-         // every warp forms the same ||theta' - theta||^2 (same order in every warp and every CTA)
-         double d2 = 0.0;
-         for (int j = lane; j < T; j += 32) { const double diff = nxt[j] - cur[j]; d2 += diff * diff; }
-         d2 = warp_sum(d2);
-         if (zf != 0.0) { status = LOCUS_ZERO_DENOM; break; }
-         if (d2 < tol2) { status = LOCUS_OK; break; }           // ||theta' - theta||_2 < tol; theta is NOT advanced
-         for (int j = tid; j < T; j += NT) {
-            const double sj = sdiv[j];
-            th[j] = (sj != 0) ? nxt[j] / sj : 0.0;
+         if (tid < 32) {
+            double d = 0.0;
+            for (int jj = lane; jj < nb; jj += 32) d += dsq[jj];
+            d = warp_sum(d);
+            if (lane < (int)CS) (CS > 1 ? cluster.map_shared_rank(d2p, (unsigned)lane) : d2p)[rank] = d;
          }
-         { double* t_ = cur; cur = nxt; nxt = t_; }
+         SBQ_TICK(5)
+         if (CS > 1) cluster.sync(); else __syncthreads();
          SBQ_TICK(6)
-         __syncthreads();
+         double d2 = 0.0;
+         for (unsigned r = 0; r < CS; ++r) d2 += d2p[r];         // same order in every thread of every CTA
+         if (d2 < tol2) { status = LOCUS_OK; break; }           // ||theta' - theta||_2 < tol; theta is NOT advanced
+         { double* t_ = cur; cur = nxt; nxt = t_; }
          SBQ_TICK(7)
       }
    }
 #ifdef SBQ_PHASE_TIMING
    if (rank == 0 && (tid == 0 || tid == NT - 32))
-      printf("locus %d tid %d iters %d resident %d csc_smem %d lpr %d lpc %d nrows %d nnz %u | E %lld or %lld col %lld csync %lld comb %lld sync %lld upd %lld sync %lld (cycles/iter)\n", l, tid, iters,
-             (int)resident, (int)csc_in_smem, lpr, lpc, nrows, nnz_c, ph[0] / iters, ph[1] / iters, ph[2] / iters, ph[3] / iters, ph[4] / iters, ph[5] / iters, ph[6] / iters, ph[7] / iters);
+      printf("setup: sort %lld jd %lld fill %lld csc %lld rowslots %lld colslots %lld\n", st[0], st[1], st[2], st[3], st[4], st[5]);
+   if (rank == 0 && (tid == 0 || tid == NT - 32))
+      printf("locus %d tid %d iters %d resident %d csc_smem %d slots %d/%d lanes %d/%d ncache %d lpr %d lpc %d nrows %d nnz %u setup %lld | E %lld or %lld col %lld csync1 %lld own %lld d2 %lld csync2 %lld chk %lld (cycles/iter)\n", l, tid, iters,
+             (int)resident, (int)csc_in_smem, (int)use_row_slots, (int)use_slots, rslot.lanes, slot.lanes, slot.ncache, lpr, lpc, nrows, nnz_c, t_setup, ph[0] / iters, ph[1] / iters, ph[2] / iters, ph[3] / iters, ph[4] / iters, ph[5] / iters, ph[6] / iters, ph[7] / iters);
 #endif
    cluster.sync();   // no CTA may exit while a peer can still read its shared memory
 
