@@ -359,9 +359,9 @@ int set_kernel_attrs(sbq_ctx* c, K kernel, size_t smem, bool nonportable) {
    return SBQ_SUCCESS;
 }
 
-template <int NT, int NCACHE>
+template <int NT, int NCACHE, int MINB>
 int launch_cluster_class_nt(sbq_ctx* c, const LaunchClass& lc, cudaStream_t st) {
-   auto kernel = em_cluster_kernel<NT, NCACHE>;
+   auto kernel = em_cluster_kernel<NT, NCACHE, MINB>;
    int rc = set_kernel_attrs(c, kernel, lc.smem, lc.cs > 8);
    if (rc) return rc;
    cudaLaunchConfig_t cfg{};
@@ -798,7 +798,7 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
       if (!serialize && used_side < N_SIDE_STREAMS) CU(cudaStreamWaitEvent(ss, c->ev_fork, 0));
       LaunchTimer& t = c->lt[2 + used_side % N_SIDE_STREAMS];
       CU(cudaEventRecord(t.e0, ss));
-      int rc = lc.lpr == CL_NT_SMALL ? launch_cluster_class_nt<CL_NT_SMALL, 0>(c, lc, ss) : launch_cluster_class_nt<CL_NT, 0>(c, lc, ss);
+      int rc = lc.lpr == CL_NT_SMALL ? launch_cluster_class_nt<CL_NT_SMALL, 0, 1>(c, lc, ss) : launch_cluster_class_nt<CL_NT, 0, 1>(c, lc, ss);
       if (rc) return rc;
       CU(cudaEventRecord(t.e1, ss));
       t.used = true;

@@ -568,7 +568,7 @@ struct ColSlot {
 };
 struct RowSlot {
    int s;                      // sorted row, or -1 for an idle thread
-   int q, lanes, wl;           // this thread is lane q of `lanes`; wl = largest group of the warp
+   int q, lanes, n;            // this thread is lane q of `lanes`; the lanes of a row are n threads apart (see assign_row_slots)
    int len;                    // entries of the row (0 for a dropped row)
    int ne;                     // n_s, or -1 for a dropped row
 };
@@ -622,6 +622,48 @@ __device__ __forceinline__ unsigned assign_slots(int n_items, int my_len, unsign
    return sl;
 }
 
+// Row slots (rows sorted by descending length, nrows <= NT): every warp serves n = 32 / L consecutive rows with L lanes
+// each, L = the lanes its first (longest) row needs for the target E. Lane l of the warp is lane q = l / n of row
+// first + l % n, so lanes with equal q read consecutive rows of one diagonal - consecutive shared-memory addresses.
+// Returns first | n << 16 | L << 24 of this thread's warp (0xffffffff for an idle warp).
+template <int NT>
+__device__ __forceinline__ unsigned assign_row_slots(const unsigned short* rlen, int nrows, unsigned total_work, unsigned* s_winfo) {
+   const int tid = threadIdx.x;
+   if (tid < 32) {
+      // lane c of warp 0 tries the target E0 * (1 + c / 8); the smallest target whose packing fits wins
+      const int E0 = max(1, (int)((total_work + NT - 1) / NT));
+      const int longest = nrows > 0 ? (int)rlen[0] : 1;
+      int E = E0 + (E0 * tid + 7) / 8;
+      if (tid == 31) E = max(E, longest);                   // one lane per row always fits (nrows <= NT)
+      int first = 0;
+      for (int w = 0; w < NT / 32 && first < nrows; ++w) first += 32 / min(32, max(1, ((int)rlen[first] + E - 1) / E));
+      const unsigned fits = __ballot_sync(0xffffffffu, first >= nrows);
+      if (tid == __ffs(fits) - 1) {
+         int f = 0, w = 0;
+         for (; w < NT / 32 && f < nrows; ++w) {
+            const int L = min(32, max(1, ((int)rlen[f] + E - 1) / E));
+            const int n = 32 / L;
+            s_winfo[w] = (unsigned)f | ((unsigned)n << 16) | ((unsigned)L << 24);
+            f += n;
+         }
+         for (; w < NT / 32; ++w) s_winfo[w] = 0xffffffffu;
+      }
+   }
+   __syncthreads();
+   const unsigned info = s_winfo[tid >> 5];
+   __syncthreads();
+   return info;
+}
+
+// fixed-shape sum over the lanes of a row (n threads apart, lane 0 of the row holds the result)
+__device__ __forceinline__ double row_sum(double v, int q, int lanes, int n) {
+   for (int o = 1; o < lanes; o <<= 1) {        // lanes is warp-uniform
+      const double u = __shfl_down_sync(0xffffffffu, v, o * n);
+      if (q + o < lanes) v += u;
+   }
+   return v;
+}
+
 // fixed-shape sum over the lanes of a slot group (consecutive lanes of one warp); lane 0 of the group holds the result.
 // wl = the largest group of this warp (warp-uniform), so warps of single-lane groups do not shuffle at all
 __device__ __forceinline__ double group_sum(double v, int q, int lanes, int wl) {
@@ -671,7 +713,7 @@ __device__ __forceinline__ void slot_e_pass(const ResidentSlice& S, const RowSlo
       d0 += v2 ? t2 : 0.0;
       d1 += v3 ? t3 : 0.0;
    }
-   const double d = group_sum(d0 + d1, rs.q, rs.lanes, rs.wl);
+   const double d = row_sum(d0 + d1, rs.q, rs.lanes, rs.n);
    if (rs.s >= 0 && rs.q == 0) {
       double r = 0.0;
       if (rs.ne >= 0) {
@@ -734,8 +776,8 @@ struct LocalOut {
    __device__ __forceinline__ double* ptr(int j) const { return out + j; }
 };
 
-template <int NT, int NCACHE>
-__global__ void __launch_bounds__(NT)
+template <int NT, int NCACHE, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, unsigned smem_bytes) {
    cg::cluster_group cluster = cg::this_cluster();
    const unsigned CS = cluster.num_blocks();
@@ -816,7 +858,7 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
    ColSlot<NCACHE> slot;
    slot.j = -1; slot.q = 0; slot.lanes = 1; slot.wl = 1; slot.x_tail = slot.x1 = 0; slot.ncache = 0; slot.out = part;
    RowSlot rslot;
-   rslot.s = -1; rslot.q = 0; rslot.lanes = 1; rslot.wl = 1; rslot.len = 0; rslot.ne = -1;
+   rslot.s = -1; rslot.q = 0; rslot.lanes = 1; rslot.n = 1; rslot.len = 0; rslot.ne = -1;
 
 #ifdef SBQ_PHASE_TIMING
    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -1021,16 +1063,21 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
       __shared__ int s_lanes[NT];
       __shared__ int s_total;
       if (use_row_slots) {
-         const int len_s = tid < nrows ? (int)S.rlen[tid] : 0;
-         const unsigned sl = assign_slots<NT>(nrows, len_s, nnz_c, s_slot, s_lanes, &s_total);
-         if (sl != 0xffffffffu) {
-            rslot.s = (int)(sl & 0xffffu);
-            rslot.q = (int)((sl >> 16) & 0xffu);
-            rslot.lanes = (int)(sl >> 24);
-            rslot.ne = S.ne[rslot.s];
-            rslot.len = rslot.ne >= 0 ? (int)S.rlen[rslot.s] : 0;
+         const unsigned info = assign_row_slots<NT>(S.rlen, nrows, nnz_c, s_slot);
+         if (info != 0xffffffffu) {
+            const int first = (int)(info & 0xffffu), n = (int)((info >> 16) & 0xffu), L = (int)(info >> 24);
+            rslot.lanes = L;
+            rslot.n = n;
+            rslot.q = lane / n;
+            const int row = first + lane % n;
+            if (rslot.q < L && row < nrows) {
+               rslot.s = row;
+               rslot.ne = S.ne[row];
+               rslot.len = rslot.ne >= 0 ? (int)S.rlen[row] : 0;
+            } else {
+               rslot.q = L;                    // idle lane: never adds, never stores
+            }
          }
-         rslot.wl = __reduce_max_sync(0xffffffffu, rslot.lanes);
       }
       SBQ_STICK(4)
       if (use_slots) {
