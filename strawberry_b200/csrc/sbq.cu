@@ -261,11 +261,21 @@ size_t cluster_class_smem(int max_iso, size_t slice_bytes, int nt) {
 int smem_bucket(size_t bytes) { return bytes <= 24 * 1024 ? 0 : bytes <= 56 * 1024 ? 1 : bytes <= 112 * 1024 ? 2 : 3; }
 
 int cluster_size_for(int64_t nnz) {
-   // ~14 B of shared memory per non-zero (CSR + CSC index): keep a CTA's slice under ~10k non-zeros
-   if (nnz <= 9 * 1024) return 1;
-   if (nnz <= 18 * 1024) return 2;
-   if (nnz <= 36 * 1024) return 4;
-   if (nnz <= 72 * 1024) return 8;
+   // ~14 B of shared memory per non-zero (row part + CSC index): keep a CTA's slice under ~10k non-zeros.
+   // SBQ_CS_THRESH="a,b,c,d" (thousands of non-zeros) overrides the four thresholds (tuning aid).
+   static int64_t th[4] = {9 * 1024, 18 * 1024, 36 * 1024, 72 * 1024};
+   static bool init = false;
+   if (!init) {
+      init = true;
+      if (const char* e = std::getenv("SBQ_CS_THRESH")) {
+         long long a, b, c2, d;
+         if (std::sscanf(e, "%lld,%lld,%lld,%lld", &a, &b, &c2, &d) == 4) { th[0] = a * 1024; th[1] = b * 1024; th[2] = c2 * 1024; th[3] = d * 1024; }
+      }
+   }
+   if (nnz <= th[0]) return 1;
+   if (nnz <= th[1]) return 2;
+   if (nnz <= th[2]) return 4;
+   if (nnz <= th[3]) return 8;
    return 16;
 }
 
@@ -798,7 +808,8 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
       if (!serialize && used_side < N_SIDE_STREAMS) CU(cudaStreamWaitEvent(ss, c->ev_fork, 0));
       LaunchTimer& t = c->lt[2 + used_side % N_SIDE_STREAMS];
       CU(cudaEventRecord(t.e0, ss));
-      int rc = lc.lpr == CL_NT_SMALL ? launch_cluster_class_nt<CL_NT_SMALL, 0, 1>(c, lc, ss) : launch_cluster_class_nt<CL_NT, 0, 1>(c, lc, ss);
+      // the 128-thread variant is capped at 128 registers so that four CTAs share an SM
+      int rc = lc.lpr == CL_NT_SMALL ? launch_cluster_class_nt<CL_NT_SMALL, 0, 4>(c, lc, ss) : launch_cluster_class_nt<CL_NT, 0, 1>(c, lc, ss);
       if (rc) return rc;
       CU(cudaEventRecord(t.e1, ss));
       t.used = true;

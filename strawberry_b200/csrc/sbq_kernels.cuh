@@ -101,6 +101,10 @@ __device__ __forceinline__ double iso_fpkm(const DevParams& p, double theta, int
 // Accumulators acc[j][lane] are lane-private (stride 33 doubles per column: conflict-free both for
 // the lane-private updates and for the per-column fixed-order sum over lanes).
 // --------------------------------------------------------------------------------------------
+#ifdef SBQ_TRACE
+__device__ __forceinline__ unsigned long long trace_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned trace_smid() { unsigned s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); return s; }
+#endif
 constexpr int WT_WARPS = 8;
 constexpr int WT_MAX_ISO = 32;
 constexpr int WT_STRIDE = 33;
@@ -122,12 +126,20 @@ em_warp_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, int ma
    const int32_t* __restrict__ col = p.col;
    const double* __restrict__ al = p.alpha;
    const double tol2 = p.tol * p.tol;
+#ifdef SBQ_TRACE
+   const unsigned long long trace_t0 = trace_now();
+#endif
 
    for (;;) {
       int w = 0;
       if (lane == 0) w = atomicAdd(queue, 1);
       w = __shfl_sync(0xffffffffu, w, 0);
-      if (w >= n_list) break;
+      if (w >= n_list) {
+#ifdef SBQ_TRACE
+         if (threadIdx.x == 0) printf("TRACE warp nt%d locus -1 rank 0 sm %u t0 %llu t1 %llu iters 0\n", WT_WARPS * 32, trace_smid(), trace_t0, trace_now());
+#endif
+         break;
+      }
       const int l = list[w];
       const int64_t r0 = p.loc_row_off[l];
       const int R = (int)(p.loc_row_off[l + 1] - r0);
@@ -785,6 +797,9 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
    const int item = blockIdx.x / CS;
    const int l = list[item];
    const int tid = threadIdx.x, lane = tid & 31;
+#ifdef SBQ_TRACE
+   const unsigned long long trace_t0 = trace_now();
+#endif
 
    const int64_t r0 = p.loc_row_off[l];
    const int R = (int)(p.loc_row_off[l + 1] - r0);
@@ -1238,6 +1253,9 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
              (int)resident, (int)csc_in_smem, (int)use_row_slots, (int)use_slots, rslot.lanes, slot.lanes, slot.ncache, lpr, lpc, nrows, nnz_c, t_setup, ph[0] / iters, ph[1] / iters, ph[2] / iters, ph[3] / iters, ph[4] / iters, ph[5] / iters, ph[6] / iters, ph[7] / iters);
 #endif
    cluster.sync();   // no CTA may exit while a peer can still read its shared memory
+#ifdef SBQ_TRACE
+   if (tid == 0) printf("TRACE c%u nt%d locus %d rank %u sm %u t0 %llu t1 %llu iters %d\n", CS, NT, l, rank, trace_smid(), trace_t0, trace_now(), iters);
+#endif
 
    if (rank != 0) return;
    // ---- outputs + epilogue (src/estimate.cpp:310-356), CTA 0 of the cluster
