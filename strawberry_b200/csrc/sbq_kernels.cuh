@@ -593,7 +593,7 @@ __device__ __forceinline__ unsigned assign_slots(int n_items, int my_len, unsign
    const int tid = threadIdx.x;
    // sum_i ceil(len_i / E) ~ total / E + n_items / 2, and a little is lost at warp boundaries
    const int budget = max(NT / 4, NT - n_items / 2 - 16);
-   int E = max(1, (int)((total_work + budget - 1) / budget));
+   int E = max(8, (int)((total_work + budget - 1) / budget));        // at least eight entries per lane: short reductions
    for (;;) {
       if (tid < n_items) s_lanes[tid] = min(32, max(1, (my_len + E - 1) / E));
       __syncthreads();
@@ -643,7 +643,7 @@ __device__ __forceinline__ unsigned assign_row_slots(const unsigned short* rlen,
    const int tid = threadIdx.x;
    if (tid < 32) {
       // lane c of warp 0 tries the target E0 * (1 + c / 8); the smallest target whose packing fits wins
-      const int E0 = max(1, (int)((total_work + NT - 1) / NT));
+      const int E0 = max(8, (int)((total_work + NT - 1) / NT));            // at least eight entries per lane: short reductions
       const int longest = nrows > 0 ? (int)rlen[0] : 1;
       int E = E0 + (E0 * tid + 7) / 8;
       if (tid == 31) E = max(E, longest);                   // one lane per row always fits (nrows <= NT)
@@ -1202,44 +1202,66 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
                *own.ptr(j) = sj;
             }
          }
-         if (tid < (int)CS) (CS > 1 ? cluster.map_shared_rank(flags, (unsigned)tid) : flags)[rank] = (double)zero;
-         if (CS > 1) cluster.sync(); else __syncthreads();
-         SBQ_TICK(3)
-         double zf = 0.0;
-         for (unsigned r = 0; r < CS; ++r) zf += flags[r];
-         if (zf != 0.0) { status = LOCUS_ZERO_DENOM; break; }
-         // owner: CS lanes per owned column, fixed butterfly; lane r pushes the result to peer r
-         {
-            const int items = nb * (int)CS;
-            const unsigned r = (unsigned)tid % CS;
-            double* peer_nxt = CS > 1 ? cluster.map_shared_rank(nxt, r) : nxt;
-            double* peer_th = CS > 1 ? cluster.map_shared_rank(th, r) : th;
-            for (int base = 0; base < items; base += NT) {
-               const int x = base + tid, jj = x / (int)CS;
-               double v = x < items ? stage[(size_t)r * B + jj] : 0.0;
-               for (unsigned o = CS >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-               if (x < items) {
-                  const int j = (int)rank * B + jj;
-                  const double sj = sdiv[j];
-                  peer_nxt[j] = v;
-                  peer_th[j] = (sj != 0) ? v / sj : 0.0;
-                  if (r == 0) { const double diff = v - cur[j]; dsq[jj] = diff * diff; }
+         double d2 = 0.0;
+         if (CS == 1) {
+            // single CTA: theta' is the stage row itself; one division per column, ||theta' - theta||^2 by warp
+            __syncthreads();
+            SBQ_TICK(3)
+            if (zero) { status = LOCUS_ZERO_DENOM; break; }
+            double dd = 0.0;
+            for (int j = tid; j < T; j += NT) {
+               const double v = stage[j], sj = sdiv[j];
+               nxt[j] = v;
+               th[j] = (sj != 0) ? v / sj : 0.0;
+               const double diff = v - cur[j];
+               dd += diff * diff;
+            }
+            if ((tid & ~31) < T) dd = warp_sum(dd);            // warps without columns hold 0 already
+            if (lane == 0) dsq[tid >> 5] = dd;
+            SBQ_TICK(4)
+            __syncthreads();
+            SBQ_TICK(6)
+#pragma unroll
+            for (int w = 0; w < NT / 32; ++w) d2 += dsq[w];      // same order in every thread
+         } else {
+            if (tid < (int)CS) cluster.map_shared_rank(flags, (unsigned)tid)[rank] = (double)zero;
+            cluster.sync();
+            SBQ_TICK(3)
+            double zf = 0.0;
+            for (unsigned r = 0; r < CS; ++r) zf += flags[r];
+            if (zf != 0.0) { status = LOCUS_ZERO_DENOM; break; }
+            // owner: CS lanes per owned column, fixed butterfly; lane r pushes the result to peer r
+            {
+               const int items = nb * (int)CS;
+               const unsigned r = (unsigned)tid % CS;
+               double* peer_nxt = cluster.map_shared_rank(nxt, r);
+               double* peer_th = cluster.map_shared_rank(th, r);
+               for (int base = 0; base < items; base += NT) {
+                  const int x = base + tid, jj = x / (int)CS;
+                  double v = x < items ? stage[(size_t)r * B + jj] : 0.0;
+                  for (unsigned o = CS >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                  if (x < items) {
+                     const int j = (int)rank * B + jj;
+                     const double sj = sdiv[j];
+                     peer_nxt[j] = v;
+                     peer_th[j] = (sj != 0) ? v / sj : 0.0;
+                     if (r == 0) { const double diff = v - cur[j]; dsq[jj] = diff * diff; }
+                  }
                }
             }
+            SBQ_TICK(4)
+            __syncthreads();
+            if (tid < 32) {
+               double d = 0.0;
+               for (int jj = lane; jj < nb; jj += 32) d += dsq[jj];
+               d = warp_sum(d);
+               if (lane < (int)CS) cluster.map_shared_rank(d2p, (unsigned)lane)[rank] = d;
+            }
+            SBQ_TICK(5)
+            cluster.sync();
+            SBQ_TICK(6)
+            for (unsigned r = 0; r < CS; ++r) d2 += d2p[r];      // same order in every thread of every CTA
          }
-         SBQ_TICK(4)
-         __syncthreads();
-         if (tid < 32) {
-            double d = 0.0;
-            for (int jj = lane; jj < nb; jj += 32) d += dsq[jj];
-            d = warp_sum(d);
-            if (lane < (int)CS) (CS > 1 ? cluster.map_shared_rank(d2p, (unsigned)lane) : d2p)[rank] = d;
-         }
-         SBQ_TICK(5)
-         if (CS > 1) cluster.sync(); else __syncthreads();
-         SBQ_TICK(6)
-         double d2 = 0.0;
-         for (unsigned r = 0; r < CS; ++r) d2 += d2p[r];         // same order in every thread of every CTA
          if (d2 < tol2) { status = LOCUS_OK; break; }           // ||theta' - theta||_2 < tol; theta is NOT advanced
          { double* t_ = cur; cur = nxt; nxt = t_; }
          SBQ_TICK(7)
