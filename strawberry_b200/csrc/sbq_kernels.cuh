@@ -999,6 +999,7 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
                   atomicAdd(&S.cp[cv + 1], 1u);
                }
             }
+            __syncwarp();   // every lane of a group has read the row's original index before lane 0 replaces it by n_s
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                int keep = keepv[r];

@@ -234,3 +234,42 @@ def test_grid_tier_dense_rows_take_the_oversize_chunk_path(q, oracle_mod):
     assert qq.stats()["loci_grid"] == 1
     assert_matches_oracle(res, ora, b, "dense-row giant locus")
     qq.close()
+
+
+def _shape_locus(rng, T, R, k_mean, empty_rows=0, dropped_rows=0):
+    """One locus with Poisson(k_mean) columns per row (clamped to 1..T), plus rows without entries and rows whose
+    alphas are all below the row filter."""
+    rows = []
+    for i in range(R):
+        k = int(min(T, max(1, rng.poisson(k_mean))))
+        c = np.sort(rng.choice(T, k, replace=False)).astype(np.int32)
+        a = 10.0 ** rng.uniform(-4, -1.5, k)
+        rows.append((c, a))
+    for _ in range(empty_rows):
+        rows.insert(int(rng.integers(0, len(rows) + 1)), (np.zeros(0, np.int32), np.zeros(0)))
+    for _ in range(dropped_rows):
+        k = int(min(T, 2))
+        rows.insert(int(rng.integers(0, len(rows) + 1)), (np.arange(k, dtype=np.int32), np.full(k, 1e-6)))
+    rp = np.concatenate([[0], np.cumsum([len(c) for c, _ in rows])]).astype(np.int64)
+    n = len(rows)
+    return dict(loc_row_off=np.array([0, n], np.int64), loc_iso_off=np.array([0, T], np.int64), row_ptr=rp,
+                col=np.concatenate([c for c, _ in rows]).astype(np.int32), alpha=np.concatenate([a for _, a in rows]),
+                count=rng.integers(1, 100, n).astype(np.int32), iso_len=rng.integers(300, 5000, T).astype(np.int32),
+                total_mapped_reads=1_000_000)
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 16])
+def test_cluster_tier_edge_shapes(q, oracle_mod, cluster):
+    """Shapes that take the less common branches of the cluster kernel: more isoforms than threads (generic M-step),
+    more rows than threads (four-rows-per-thread E-step), a slice too large for shared memory (streaming fallback),
+    empty and dropped rows, a single isoform, rows as long as T."""
+    rng = np.random.default_rng(77)
+    shapes = [dict(T=600, R=400, k_mean=40), dict(T=20, R=3000, k_mean=3), dict(T=100, R=3000, k_mean=30),
+              dict(T=5, R=40, k_mean=2, empty_rows=7, dropped_rows=9), dict(T=1, R=10, k_mean=1),
+              dict(T=700, R=40, k_mean=650), dict(T=40, R=700, k_mean=12, empty_rows=3), dict(T=33, R=33, k_mean=33)]
+    b = synth.concat([_shape_locus(rng, **s) for s in shapes])
+    b["total_mapped_reads"] = 1_000_000
+    ora = oracle_mod.quantify_batch(b, b["total_mapped_reads"])
+    res = run_gpu(q, b, 2, cluster)
+    assert_matches_oracle(res, ora, b, f"edge shapes, cluster {cluster}")
+    assert res["stats"]["loci_cta"] == len(shapes)
