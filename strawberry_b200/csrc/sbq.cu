@@ -261,9 +261,11 @@ size_t cluster_class_smem(int max_iso, size_t slice_bytes, int nt) {
 int smem_bucket(size_t bytes) { return bytes <= 24 * 1024 ? 0 : bytes <= 56 * 1024 ? 1 : bytes <= 112 * 1024 ? 2 : 3; }
 
 int cluster_size_for(int64_t nnz) {
-   // ~14 B of shared memory per non-zero (row part + CSC index): keep a CTA's slice under ~10k non-zeros.
+   // ~14 B of shared memory per non-zero (row part + CSC index): a CTA's slice stays under ~14k non-zeros, which still
+   // fits with its CSC index. Smaller clusters cost latency per iteration (fewer SMs per locus) but less SM time in
+   // total; these thresholds were the best of a sweep on the human-shaped workload (profiles/r01_cluster_thresholds.txt).
    // SBQ_CS_THRESH="a,b,c,d" (thousands of non-zeros) overrides the four thresholds (tuning aid).
-   static int64_t th[4] = {9 * 1024, 18 * 1024, 36 * 1024, 72 * 1024};
+   static int64_t th[4] = {12 * 1024, 24 * 1024, 48 * 1024, 112 * 1024};
    static bool init = false;
    if (!init) {
       init = true;
