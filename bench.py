@@ -307,15 +307,16 @@ def main():
                 qg.finalize_tpm(qg.fpkm_sum())
                 qg.download()
                 gst = qg.stats()
+                g_kernel = next((r["kernel"] for r in qg.launch_stats() if r["kernel"].startswith("em_grid")), "em_grid_kernel")
                 g_ach = gst["grid_alg_bytes"] / (float(np.mean(g_ms)) * 1e-3) / 1e9
-                # DRAM bytes per non-zero and pass measured by ncu --set full on this kernel (profiles/r01_grid_tma_ncu_summary.txt:
-                # dram__bytes_read.sum + write = 4.47 GB for 9 passes over 48.0 M non-zeros = 10.3 B; the kernel streams u16
-                # columns, so it moves LESS than the 12 B/nnz the roofline counts as algorithmic)
+                # DRAM bytes per non-zero and pass measured by ncu --set full on these kernels (profiles/r01_grid_dual_ncu_summary.txt:
+                # dram__bytes_read.sum + write = 4.59 GB for 9 passes over 48.0 M non-zeros = 10.6 B; r01_grid_tma_ncu_summary.txt:
+                # 10.3 B): u16 columns are streamed, so the kernels move LESS than the 12 B/nnz the roofline counts as algorithmic
                 passes = gst["em_iters_total"] + args.giant_loci
-                g_traffic = 10.34 * (gst["nnz"] / args.giant_loci) * passes
+                g_traffic = (10.63 if g_kernel == "em_grid_dual_kernel" else 10.34) * (gst["nnz"] / args.giant_loci) * passes
                 line["roofline_giant"] = {"bound": "hbm", "achieved": g_ach, "peak": peak, "unit": "GB/s", "frac": g_ach / peak,
-                                          "traffic": g_traffic, "traffic_source": "scaled from the ncu --set full capture of the same kernel in profiles/ (10.34 B per non-zero and pass)",
-                                          "kernel": "em_grid_tma_kernel", "kernel_ms": float(np.mean(g_ms)),
+                                          "traffic": g_traffic, "traffic_source": "scaled from the ncu --set full capture of the same kernel in profiles/ (bytes per non-zero and pass)",
+                                          "kernel": g_kernel, "kernel_ms": float(np.mean(g_ms)),
                                           "alg_bytes_per_launch": gst["grid_alg_bytes"], "peak_source": peak_src,
                                           "workload": f"configs[3] shape: {args.giant_loci} loci x {args.giant_rows} rows, n_i=1, k~1+Poisson(47), T~U{{500..800}} "
                                                       f"({gst['nnz']} nnz, {gst['em_iters_total']} EM iterations in total); CSR {gst['nnz'] * 12 / 1e9:.2f} GB > L2",

@@ -168,7 +168,7 @@ typedef struct {
    int32_t kind;            /* 1 = warp tier, 2 = cluster tier, 3 = grid (giant-locus) tier               */
    int32_t cluster_size;    /* CTAs per locus (cluster tier)                                              */
    int32_t lanes_per_row;
-   int32_t reserved;
+   int32_t variant;         /* grid tier: 1 = register-staged loads, 2 = TMA ring, 3 = bank-aligned two-slot layout */
    int64_t n_loci, nnz;
    double  ms;              /* kernel duration                                                            */
    int64_t alg_bytes;       /* sum over its loci of (12 nnz + 12 R + 16 T) * iters                         */

@@ -63,7 +63,7 @@ class Stats(ctypes.Structure):
 
 class LaunchStat(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int32), ("cluster_size", ctypes.c_int32), ("lanes_per_row", ctypes.c_int32),
-                ("reserved", ctypes.c_int32), ("n_loci", ctypes.c_int64), ("nnz", ctypes.c_int64), ("ms", ctypes.c_double),
+                ("variant", ctypes.c_int32), ("n_loci", ctypes.c_int64), ("nnz", ctypes.c_int64), ("ms", ctypes.c_double),
                 ("alg_bytes", ctypes.c_int64), ("frag_iters", ctypes.c_int64), ("max_iters", ctypes.c_int64)]
 
 
@@ -266,7 +266,8 @@ class Quantifier:
         buf = (LaunchStat * 32)()
         n = self._chk(self._L.sbq_get_launch_stats(self._h, buf, 32))
         names = {1: "em_warp_kernel", 2: "em_cluster_kernel", 3: "em_grid_kernel"}
-        return [dict(kernel=names[buf[i].kind], cluster_size=buf[i].cluster_size, lanes_per_row=buf[i].lanes_per_row,
+        grid = {1: "em_grid_kernel", 2: "em_grid_tma_kernel", 3: "em_grid_dual_kernel"}
+        return [dict(kernel=grid.get(buf[i].variant, names[buf[i].kind]) if buf[i].kind == 3 else names[buf[i].kind], cluster_size=buf[i].cluster_size, lanes_per_row=buf[i].lanes_per_row,
                      n_loci=buf[i].n_loci, nnz=buf[i].nnz, ms=buf[i].ms, alg_bytes=buf[i].alg_bytes,
                      frag_iters=buf[i].frag_iters, max_iters=buf[i].max_iters) for i in range(min(n, 32))]
 

@@ -1,0 +1,751 @@
+// sbq_grid_dual.cuh - Tier 3, fast path: multi-CTA streaming EM for giant loci over a BANK-ALIGNED, TWO-CHOICE row layout.
+//
+// The TMA ring kernel of sbq_grid_tma.cuh is bound by the shared-memory pipe, not by HBM: the theta gather and the
+// accumulator read-modify-write are 64-bit accesses indexed by column, and the 16 lanes of a half-warp that work on
+// one row hit the 16 eight-byte banks unevenly - the fullest bank of a 48-entry row holds ~7 entries where 3 would be
+// ideal, so every such access costs ~7 wavefronts instead of 3. This kernel removes the conflicts by construction:
+//
+//  * TWO SLOTS PER COLUMN. theta and the warp-private accumulators are kept twice: slot A(j) = j (bank j mod 16) and
+//    slot B(j) = Tp + 16*(j/16) + ((j + j/16) mod 16) (the column's 16-block rotated by the block index: a different
+//    bank). Every non-zero may use either slot of its column, which turns "48 balls into 16 bins" into a two-choice
+//    allocation: the fullest bank drops from ~7 to ~3.85 entries.
+//  * dual_prepare_kernel (once per upload, one warp per row) picks the slot of every non-zero (greedy least-loaded
+//    bank + two improvement sweeps) and re-sorts the row IN PLACE inside its CSR range into a jagged-diagonal order:
+//    step-major, within a step one entry per bank, banks ranked by load. Lane x of a half-warp then only ever touches
+//    bank rank x: the alpha / column reads are contiguous and the theta gather and the accumulator update are
+//    conflict-free. The u16 column copy holds the slot; a 16-byte record per row holds the per-step entry counts, the
+//    effective count and the row's offset (it replaces row pointer + count in the stream: same bytes).
+//  * em_grid_dual_kernel: persistent cooperative kernel, one CTA per SM = NC consumer warps + 1 producer warp. The
+//    producer streams 8-row chunks (alpha slab, u16 slab, record slab - three 1-D TMA bulk copies) into an NS-deep
+//    shared-memory ring; consumer warp w takes every NC-th chunk (teams of more warps per chunk are a template
+//    parameter), all 8 rows of it (four per half-warp, all in flight together: the loads of the four rows overlap, registers hold the products between
+//    the normaliser and the update). The two half-warps take turns on the warp-private accumulators (their rows may
+//    share a column), four rows one after the other.
+//  * reductions (warp-private accumulators -> per-CTA partial -> column owners -> theta') are those of the other grid
+//    kernels: fixed order, no floating-point atomics. Both slots of a column are summed there.
+//
+// Rows with more than 96 non-zeros or whose fullest bank still holds more than 6 entries keep their CSR order (flag in
+// the record) and are walked by a whole warp from global memory, as are the rows of a chunk fuller than a stage.
+// Eligibility (host planner): T <= 32760, locus non-zeros < 2^32, on average <= 56 non-zeros per row, shared memory for
+// at least 3 consumer warps. Anything else runs on em_grid_tma_kernel / em_grid_kernel.
+#pragma once
+#include "sbq_grid_tma.cuh"
+
+namespace sbq {
+
+constexpr int G6_LMAX = 6;                       // steps of the register path (fullest bank of a row)
+constexpr int G6_MAXROW = 96;                    // longest row the sorted layout takes
+constexpr unsigned char G6_FLAG = 255;           // cnt[0] of a row left in CSR order
+
+struct __align__(16) RowRec {
+   unsigned char cnt[8];     // cnt[e], e < 6: entries of step e (<= 16, descending); cnt[7]: number of steps
+   int32_t neff;             // effective count (-1: dropped by the row filter)
+   uint32_t koff;            // first non-zero of the row, relative to the locus' first non-zero
+};
+static_assert(sizeof(RowRec) == 16, "one 16-byte unit per row");
+
+constexpr int G6_NR = 4;                         // rows a half-warp keeps in flight
+constexpr int G6_MAX_SPW = 4;                    // ring stages per warp (at most)
+constexpr int G6_MAX_WARPS = 16;
+constexpr int G6_MAX_ISO = 32760;
+
+__host__ __device__ __forceinline__ int g6_tp(int T) { return (T + 15) & ~15; }
+__host__ __device__ __forceinline__ int g6_slot_b(int j, int Tp) { return Tp + (j & ~15) + ((j + (j >> 4)) & 15); }
+
+// Geometry: NC warps per CTA, every one a consumer that also streams its own chunks: warp w takes the chunks
+// w, w + NC, ... of the CTA (8 rows each) and owns SPW private ring stages. After a chunk is done its stage is refilled
+// with the warp's chunk SPW turns ahead (three 1-D bulk copies issued by lane 0) - no producer warp, no "empty"
+// barriers. (A dedicated producer thread tops out at one 8-row chunk per ~860 cycles - 90 cycles per try_wait plus the
+// copies - which caps the kernel at 0.37 ms per pass; measured.)
+template <int NC>
+struct G6Cfg {
+   static constexpr int CONSUMERS = NC;
+   static constexpr int NT = NC * 32;
+   static constexpr int CROWS = 2 * G6_NR;                // rows per chunk (four per half-warp)
+   static constexpr int CAP = CROWS * 56;                 // non-zeros a stage holds; fuller chunks are read from global memory
+   // stage layout (bytes): alpha | col16 | records
+   static constexpr int A_BYTES = (CAP + 2 + 16) * 8;     // + slack: lanes past a step's last entry still read (and discard) 8 bytes
+   static constexpr int C_OFF = A_BYTES;
+   static constexpr int C_BYTES = (((CAP + 8 + 16) * 2 + 15) / 16) * 16;
+   static constexpr int R_OFF = C_OFF + C_BYTES;
+   static constexpr int R_BYTES = (CROWS + 1) * (int)sizeof(RowRec);   // + the record after the chunk (its offset ends the chunk)
+   static constexpr int STAGE_BYTES = ((R_OFF + R_BYTES + 127) / 128) * 128;
+   static size_t fixed_bytes(int T) { return (size_t)(2 * g6_tp(T) + 16) * (1 + NC) * sizeof(double); }   // th2[2Tp+16] | acc[NC][2Tp+16]
+   static int stages_per_warp(int T) {   // ring depth per warp that fits beside the accumulators
+      const long long room = 225LL * 1024 - (long long)fixed_bytes(T);
+      long long spw = room / ((long long)STAGE_BYTES * NC);
+      if (spw > G6_MAX_SPW) spw = G6_MAX_SPW;
+      return (int)spw;
+   }
+   static bool fits(int T, int spw_min = 2) { return stages_per_warp(T) >= spw_min; }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// prepare: one warp per row
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dual_prepare_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, const int64_t* __restrict__ rec_off, RowRec* __restrict__ recs,
+                    unsigned short* __restrict__ col16) {
+   struct Scratch {
+      unsigned char bank_a[G6_MAXROW], bank_b[G6_MAXROW], pick[G6_MAXROW], seq[G6_MAXROW];
+      int load[16], pos[16], pre[G6_LMAX + 1], ok;
+   };
+   __shared__ Scratch sc_all[8];
+   const int lane = threadIdx.x & 31;
+   Scratch& sc = sc_all[threadIdx.x >> 5];
+   const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+   double* alpha = const_cast<double*>(p.alpha);
+   for (int item = 0; item < n_list; ++item) {
+      const int l = list[item];
+      const int64_t r0 = p.loc_row_off[l];
+      const int64_t R = p.loc_row_off[l + 1] - r0;
+      const int T = (int)(p.loc_iso_off[l + 1] - p.loc_iso_off[l]);
+      const int Tp = g6_tp(T);
+      const int64_t* __restrict__ rp = p.row_ptr + r0;
+      const int64_t kbase = rp[0];
+      RowRec* rec_l = recs + rec_off[item];
+      if (wid == 0 && lane < 8) {   // sentinel record R: its offset closes the last chunk
+         rec_l[R].cnt[lane] = 0;
+         if (lane == 0) { rec_l[R].neff = -1; rec_l[R].koff = (uint32_t)(rp[R] - kbase); }
+      }
+      for (int64_t row = wid; row < R; row += nw) {
+         const int64_t k0 = rp[row], k1 = rp[row + 1];
+         RowRec* rec = rec_l + row;
+         const int64_t n64 = k1 - k0;
+         bool sorted = n64 <= G6_MAXROW;
+         double a[3];
+         int c[3];
+         if (sorted) {
+            const int n = (int)n64;
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+               const int idx = lane + 32 * m;
+               const bool v = idx < n;
+               a[m] = v ? alpha[k0 + idx] : 0.0;
+               c[m] = v ? p.col[k0 + idx] : 0;
+               if (v) {
+                  sc.bank_a[idx] = (unsigned char)(c[m] & 15);
+                  sc.bank_b[idx] = (unsigned char)((c[m] + (c[m] >> 4)) & 15);
+               }
+            }
+            if (lane < 16) sc.load[lane] = 0;
+            __syncwarp();
+            if (lane == 0) {
+               // two-choice allocation: greedy least-loaded bank, then two sweeps that move an entry to its other bank when
+               // that lowers the larger of the two loads
+               for (int e = 0; e < n; ++e) {
+                  const int ba = sc.bank_a[e], bb = sc.bank_b[e];
+                  const int pk = sc.load[bb] < sc.load[ba];
+                  sc.pick[e] = (unsigned char)pk;
+                  ++sc.load[pk ? bb : ba];
+               }
+               for (int sweep = 0; sweep < 2; ++sweep) {
+                  for (int e = 0; e < n; ++e) {
+                     const int ba = sc.bank_a[e], bb = sc.bank_b[e];
+                     const int cur = sc.pick[e] ? bb : ba, alt = sc.pick[e] ? ba : bb;
+                     if (sc.load[cur] > sc.load[alt] + 1) { --sc.load[cur]; ++sc.load[alt]; sc.pick[e] ^= 1; }
+                  }
+               }
+               int L = 0;
+               for (int b = 0; b < 16; ++b) L = max(L, sc.load[b]);
+               sc.ok = L <= G6_LMAX;
+               if (sc.ok) {
+                  // banks ranked by (load desc, bank asc) -> lane position; per-step entry counts and their prefix
+                  for (int b = 0; b < 16; ++b) {
+                     int ps = 0;
+                     for (int y = 0; y < 16; ++y) ps += (sc.load[y] > sc.load[b]) || (sc.load[y] == sc.load[b] && y < b);
+                     sc.pos[b] = ps;
+                  }
+                  int acc = 0;
+                  for (int s = 0; s <= G6_LMAX; ++s) {
+                     sc.pre[s] = acc;
+                     int cn = 0;
+                     for (int b = 0; b < 16; ++b) cn += sc.load[b] > s;
+                     acc += cn;
+                  }
+                  int fill[16];
+#pragma unroll
+                  for (int b = 0; b < 16; ++b) fill[b] = 0;
+                  for (int e = 0; e < n; ++e) {
+                     const int bk = sc.pick[e] ? sc.bank_b[e] : sc.bank_a[e];
+                     int sq = 0;
+#pragma unroll
+                     for (int b = 0; b < 16; ++b)
+                        if (b == bk) sq = fill[b]++;
+                     sc.seq[e] = (unsigned char)sq;
+                  }
+               }
+            }
+            __syncwarp();
+            sorted = sc.ok != 0;
+         }
+         if (!sorted) {
+            // left in CSR order with plain (slot A) columns; the EM kernel walks it from global memory
+            for (int64_t k = k0 + lane; k < k1; k += 32) col16[k] = (unsigned short)p.col[k];
+            if (lane < 8) rec->cnt[lane] = lane == 0 ? G6_FLAG : 0;
+            if (lane == 0) { rec->neff = -1; rec->koff = (uint32_t)(k0 - kbase); }
+            __syncwarp();
+            continue;
+         }
+         const int n = (int)n64;
+#pragma unroll
+         for (int m = 0; m < 3; ++m) {
+            const int idx = lane + 32 * m;
+            if (idx < n) {
+               const int pk = sc.pick[idx];
+               const int bk = pk ? sc.bank_b[idx] : sc.bank_a[idx];
+               const int dest = sc.pre[sc.seq[idx]] + sc.pos[bk];
+               alpha[k0 + dest] = a[m];
+               col16[k0 + dest] = (unsigned short)(pk ? g6_slot_b(c[m], Tp) : c[m]);
+            }
+         }
+         if (lane < 8) {
+            int v = 0;
+            if (lane < G6_LMAX) v = sc.pre[lane + 1] - sc.pre[lane];
+            else if (lane == 7) { for (int s = 0; s < G6_LMAX; ++s) v += sc.pre[s + 1] > sc.pre[s]; }
+            rec->cnt[lane] = (unsigned char)v;
+         }
+         if (lane == 0) { rec->neff = -1; rec->koff = (uint32_t)(k0 - kbase); }
+         __syncwarp();
+      }
+   }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// consumer side
+// ------------------------------------------------------------------------------------------------------------------
+struct G6Ring {      // the private ring of one warp
+   char* stage;      // spw stages
+   uint64_t* full;   // [spw]
+   int spw;
+   unsigned used;    // chunks this warp has consumed so far (all passes): stage = used % spw, parity = (used / spw) & 1
+};
+
+__device__ __forceinline__ double g6_half_sum(double v) {   // sum over the 16 lanes of a half-warp
+#pragma unroll
+   for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+   return v;
+}
+
+// A row walked by the whole warp straight from global memory (any entry order; columns are slots).
+template <bool SETUP>
+__device__ __forceinline__ void g6_walk_row(const DevParams& p, const unsigned short* __restrict__ col16, RowRec* rec_g, int64_t a, int64_t b, int n_i,
+                                            int32_t* neff_row, const double* th2, double* my, long long& tot, long long& kept, int& zero) {
+   const int lane = threadIdx.x & 31;
+   if (SETUP) {
+      bool keep = false;
+      for (int64_t k = a + lane; k < b; k += 32) keep |= p.alpha[k] > p.row_eps;
+      keep = __any_sync(0xffffffffu, keep);
+      if (lane == 0) { rec_g->neff = keep ? n_i : -1; *neff_row = keep ? n_i : -1; tot += n_i; kept += keep; }
+      if (keep)
+         for (int64_t k = a + lane; k < b; k += 32) my[col16[k]] += p.alpha[k];
+   } else {
+      const int ne = rec_g->neff;
+      if (ne >= 0) {
+         double d = 0.0;
+         for (int64_t k = a + lane; k < b; k += 32) d += p.alpha[k] * th2[col16[k]];
+         d = warp_sum(d);
+         if (d == 0) {
+            zero = 1;
+         } else {
+            const double rr = (double)ne / d;
+            for (int64_t k = a + lane; k < b; k += 32) { const int cc = col16[k]; my[cc] += p.alpha[k] * th2[cc] * rr; }
+         }
+      }
+   }
+   __syncwarp();
+}
+
+// One warp turn on a staged chunk: G6_NR rows per half-warp, all in flight. rec0: record of the half-warp's first row in
+// the stage; n_here: how many of its G6_NR rows exist. a_s / c_s: entry 0 of the chunk in the stage. Returns the mask of
+// rows (bit q, this half-warp) that must be walked instead (flagged).
+//
+// Branch-free inner steps: a lane that holds no entry in a step works on its DUMMY slot instead - slot 2 Tp + (bank of
+// the lane's step-0 entry), which lies in the lane's own bank (no conflict with the other lanes), reads theta = 0 and
+// accumulates zeros. Lanes without any entry in the row (fewer than 16 banks used) sit the row out.
+template <bool SETUP, int LS, typename Refill>
+__device__ __forceinline__ void g6_turn_steps(const DevParams& p, const double* __restrict__ a_s, const unsigned short* __restrict__ c_s, const unsigned (&cw0)[G6_NR],
+                                              const unsigned (&cw1)[G6_NR], unsigned (&kk)[G6_NR], const int (&ne)[G6_NR], unsigned flagged, RowRec* rec_g0,
+                                              const int32_t* cnt_g0, int32_t* neff_g0, int n_here, int dummy0, const double* th2, double* my, long long& tot,
+                                              long long& kept, int& zero, Refill& refill) {
+   const int lane = threadIdx.x & 31, x = lane & 15;
+   const bool is_lo = lane < 16;
+   double pr[G6_NR][LS];          // alpha (SETUP) or alpha * theta
+   unsigned so[G6_NR][LS];        // slot * 8: byte offset into theta (th2) and into the accumulator row (my)
+#pragma unroll
+   for (int q = 0; q < G6_NR; ++q) {
+      int dummy = dummy0;
+#pragma unroll
+      for (int e = 0; e < LS; ++e) {
+         const unsigned ce = ((e < 4 ? cw0[q] : cw1[q]) >> (8 * (e & 3))) & 0xffu;
+         const bool valid = (unsigned)x < ce;
+         const double a = a_s[kk[q]];
+         const int c = (int)c_s[kk[q]];
+         if (e == 0) dummy = dummy0 + (valid ? (c & 15) : x);   // a lane without any entry in the row: a bank of its own choice (rare extra wavefront)
+         pr[q][e] = (SETUP && !valid) ? 0.0 : a;   // EM: a lane without an entry reads a finite stale alpha and multiplies it by theta[dummy] = 0
+         so[q][e] = (unsigned)(valid ? c : dummy) << 3;
+         kk[q] += ce;
+      }
+   }
+   // everything this turn needs from the stage now sits in registers: the stage can be refilled while the turn computes
+   __syncwarp();
+   refill();
+   const char* th2b = reinterpret_cast<const char*>(th2);
+   char* myb = reinterpret_cast<char*>(my);
+   // E-phase
+   double r[G6_NR];
+   if (SETUP) {
+#pragma unroll
+      for (int q = 0; q < G6_NR; ++q) {
+         bool big = false;
+#pragma unroll
+         for (int e = 0; e < LS; ++e) big |= pr[q][e] > p.row_eps;
+         const unsigned bal = __ballot_sync(0xffffffffu, big);
+         const bool keep = ((bal >> (lane & 16)) & 0xffffu) != 0;
+         r[q] = keep ? 1.0 : 0.0;
+         if (x == 0 && q < n_here && !((flagged >> q) & 1u)) {
+            const int n = cnt_g0[q];
+            rec_g0[q].neff = keep ? n : -1;
+            neff_g0[q] = keep ? n : -1;
+            tot += n;
+            kept += keep;
+         }
+      }
+   } else {
+      double d[G6_NR];
+#pragma unroll
+      for (int q = 0; q < G6_NR; ++q) {
+         d[q] = 0.0;
+#pragma unroll
+         for (int e = 0; e < LS; ++e) {
+            pr[q][e] *= *reinterpret_cast<const double*>(th2b + so[q][e]);
+            d[q] += pr[q][e];
+         }
+      }
+#pragma unroll
+      for (int q = 0; q < G6_NR; ++q) d[q] = g6_half_sum(d[q]);
+#pragma unroll
+      for (int q = 0; q < G6_NR; ++q) {
+         r[q] = 0.0;
+         if (ne[q] >= 0) {
+            if (d[q] == 0) zero = 1;
+            else r[q] = (d[q] > 1e-290 && d[q] < 1e290) ? fast_div_pos((double)ne[q], d[q]) : (double)ne[q] / d[q];
+         }
+      }
+   }
+   // M-phase: rows in order (two rows of a half-warp may share a column), inside a row the low half-warp first. A row's
+   // slots are distinct, so its loads are issued together, then its stores.
+#pragma unroll
+   for (int q = 0; q < G6_NR; ++q) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+         if ((h == 0) == is_lo) {
+            double o[LS];
+#pragma unroll
+            for (int e = 0; e < LS; ++e) o[e] = *reinterpret_cast<double*>(myb + so[q][e]);
+#pragma unroll
+            for (int e = 0; e < LS; ++e) *reinterpret_cast<double*>(myb + so[q][e]) = fma(pr[q][e], r[q], o[e]);
+         }
+         __syncwarp();
+      }
+   }
+}
+
+template <bool SETUP, typename Refill>
+__device__ __forceinline__ unsigned g6_turn(const DevParams& p, const double* __restrict__ a_s, const unsigned short* __restrict__ c_s, const RowRec* rec0,
+                                            RowRec* rec_g0, const int32_t* cnt_g0, int32_t* neff_g0, int n_here, uint32_t ck0, int dummy0,
+                                            const double* th2, double* my, long long& tot, long long& kept, int& zero, Refill refill) {
+   const int x = threadIdx.x & 15;
+   int ne[G6_NR];
+   unsigned flagged = 0;
+   int L = 0;
+   unsigned cw0[G6_NR], cw1[G6_NR], kk[G6_NR];
+#pragma unroll
+   for (int q = 0; q < G6_NR; ++q) {
+      const bool ex = q < n_here;
+      const uint2 cw = ex ? *reinterpret_cast<const uint2*>(rec0[q].cnt) : make_uint2(0u, 0u);
+      const uint2 nk = ex ? *reinterpret_cast<const uint2*>(&rec0[q].neff) : make_uint2(0xffffffffu, ck0);
+      const bool fl = (cw.x & 0xffu) == G6_FLAG;
+      if (fl) flagged |= 1u << q;
+      ne[q] = fl ? -1 : (int)nk.x;
+      cw0[q] = fl ? 0u : cw.x;
+      cw1[q] = fl ? 0u : cw.y;
+      L = max(L, (int)(cw1[q] >> 24));
+      kk[q] = nk.y - ck0 + x;
+   }
+   L = max(L, __shfl_xor_sync(0xffffffffu, L, 16));   // steps of the longest of the warp's eight rows
+   // straight-line bodies for 4, 5 and 6 steps (a row's fullest bank holds 4 entries in ~70 % of the rows, 5 in most others)
+   if (SETUP || L > 5) g6_turn_steps<SETUP, 6>(p, a_s, c_s, cw0, cw1, kk, ne, flagged, rec_g0, cnt_g0, neff_g0, n_here, dummy0, th2, my, tot, kept, zero, refill);
+   else if (L == 5) g6_turn_steps<SETUP, 5>(p, a_s, c_s, cw0, cw1, kk, ne, flagged, rec_g0, cnt_g0, neff_g0, n_here, dummy0, th2, my, tot, kept, zero, refill);
+   else g6_turn_steps<SETUP, 4>(p, a_s, c_s, cw0, cw1, kk, ne, flagged, rec_g0, cnt_g0, neff_g0, n_here, dummy0, th2, my, tot, kept, zero, refill);
+   return flagged;
+}
+
+// Lane 0: start the three bulk copies of CTA-local chunk c into stage `st` (k0, k1: its non-zero range, absolute).
+template <typename C>
+__device__ __forceinline__ void g6_issue(const DevParams& p, const unsigned short* __restrict__ col16, const RowRec* __restrict__ rec_cta, int n_rows, int c,
+                                         int64_t k0, int64_t k1, char* st, uint64_t* full) {
+   const bool staged = k1 - k0 <= (int64_t)C::CAP;   // a fuller chunk only brings its records
+   const int64_t ka = k0 & ~(int64_t)1, kc = k0 & ~(int64_t)7;
+   const unsigned a_bytes = staged ? (unsigned)(((k1 - ka + 1) & ~(int64_t)1) * 8) : 0u;
+   const unsigned c_bytes = staged ? (unsigned)(((k1 - kc + 7) & ~(int64_t)7) * 2) : 0u;
+   const int i0 = c * C::CROWS, i1 = min(i0 + C::CROWS, n_rows);
+   const unsigned r_bytes = (unsigned)((i1 - i0 + 1) * sizeof(RowRec));
+   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stage was last read with ordinary shared-memory loads
+   mbar_expect_tx(full, a_bytes + c_bytes + r_bytes);
+   if (a_bytes) bulk_g2s(st, p.alpha + ka, a_bytes, full);
+   if (c_bytes) bulk_g2s(st + C::C_OFF, col16 + kc, c_bytes, full);
+   bulk_g2s(st + C::R_OFF, rec_cta + i0, r_bytes, full);
+}
+
+// One pass of this warp over its chunks (w, w + NC, ...) of the CTA's rows.
+template <typename C, bool SETUP>
+__device__ __forceinline__ void g6_pass(const DevParams& p, const unsigned short* __restrict__ col16, RowRec* __restrict__ rec_cta /* row 0 of this CTA */,
+                                        const int64_t* __restrict__ rp_cta /* row pointer of the CTA's row 0 */, const int64_t kbase /* first non-zero of the locus */,
+                                        int64_t row_abs0 /* absolute row of the CTA's row 0 */, int n_rows, int n_chunk, G6Ring& ring,
+                                        int dummy0 /* first dummy slot = 2 Tp */, const double* th2, double* my, long long& tot, long long& kept, int& zero) {
+   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   const int n_mine = warp < n_chunk ? (n_chunk - warp + C::CONSUMERS - 1) / C::CONSUMERS : 0;
+   // prologue: fill the ring (records written with ordinary global stores in the setup pass are read by bulk copies)
+   asm volatile("fence.proxy.async;" ::: "memory");
+   if (lane == 0) {
+      for (int i = 0; i < min(ring.spw, n_mine); ++i) {
+         const int c = warp + i * C::CONSUMERS;
+         const unsigned u = ring.used + (unsigned)i;
+         g6_issue<C>(p, col16, rec_cta, n_rows, c, rp_cta[min(c * C::CROWS, n_rows)], rp_cta[min((c + 1) * C::CROWS, n_rows)],
+                     ring.stage + (size_t)(u % (unsigned)ring.spw) * C::STAGE_BYTES, &ring.full[u % (unsigned)ring.spw]);
+      }
+   }
+   __syncwarp();
+   for (int i = 0; i < n_mine; ++i) {
+      const int c = warp + i * C::CONSUMERS;
+      const unsigned u = ring.used + (unsigned)i;
+      const int sidx = (int)(u % (unsigned)ring.spw);
+      // boundaries of the chunk that will refill this stage, fetched now so that the loads overlap the turn
+      const int cn = c + ring.spw * C::CONSUMERS;
+      int64_t kn0 = 0, kn1 = 0;
+      if (lane == 0 && cn < n_chunk) { kn0 = rp_cta[min(cn * C::CROWS, n_rows)]; kn1 = rp_cta[min((cn + 1) * C::CROWS, n_rows)]; }
+      const int i0 = c * C::CROWS, i1 = min(i0 + C::CROWS, n_rows);       // rows of the chunk (CTA-local)
+      mbar_wait(&ring.full[sidx], (u / (unsigned)ring.spw) & 1u);
+      char* st = ring.stage + (size_t)sidx * C::STAGE_BYTES;
+      const RowRec* rec_s = (const RowRec*)(st + C::R_OFF);
+      const uint32_t ck0 = rec_s[0].koff;
+      const uint32_t ck1 = rec_s[i1 - i0].koff;
+      const bool staged = ck1 - ck0 <= (uint32_t)C::CAP;   // same decision as g6_issue
+      const int h0 = i0 + (lane >> 4) * G6_NR;             // first row of this half-warp
+      unsigned walk = 0;                                   // bit i: row i0 + i is walked from global memory
+      auto refill = [&]() {
+         if (lane == 0 && cn < n_chunk) g6_issue<C>(p, col16, rec_cta, n_rows, cn, kn0, kn1, st, &ring.full[sidx]);
+      };
+      if (staged) {
+         const int64_t k0 = kbase + ck0;
+         const unsigned fl = g6_turn<SETUP>(p, (const double*)st + (k0 & 1), (const unsigned short*)(st + C::C_OFF) + (k0 & 7), rec_s + (min(h0, i1 - 1) - i0),
+                                            rec_cta + h0, p.count + row_abs0 + h0, p.neff + row_abs0 + h0, max(0, min(G6_NR, i1 - h0)), ck0, dummy0, th2, my,
+                                            tot, kept, zero, refill);
+         walk = __shfl_sync(0xffffffffu, fl, 0) | (__shfl_sync(0xffffffffu, fl, 16) << G6_NR);
+      } else {
+         walk = (1u << C::CROWS) - 1u;
+         __syncwarp();
+         refill();
+      }
+      while (walk) {
+         const int r = __ffs(walk) - 1;
+         walk &= walk - 1;
+         const int row = i0 + r;
+         if (row < i1)
+            g6_walk_row<SETUP>(p, col16, rec_cta + row, rp_cta[row], rp_cta[row + 1], SETUP ? p.count[row_abs0 + row] : 0, p.neff + row_abs0 + row, th2, my,
+                               tot, kept, zero);
+      }
+   }
+   ring.used += (unsigned)n_mine;
+}
+
+template <typename C>
+__global__ void __launch_bounds__(C::NT, 1)
+em_grid_dual_kernel(DevParams p, const unsigned short* __restrict__ col16, RowRec* __restrict__ recs, const int64_t* __restrict__ rec_off,
+                    const int32_t* __restrict__ list, int n_list, GridScratch gs, double* cur_glob /* [n_cta][tstride] */, int spw) {
+   cg::grid_group grid = cg::this_grid();
+   extern __shared__ __align__(128) unsigned char g6_smem[];
+   __shared__ double red[C::NT / 32];
+   __shared__ int s_rows[2];
+   __shared__ __align__(8) uint64_t s_bar[G6_MAX_WARPS * G6_MAX_SPW];
+   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+   const int nb = gridDim.x, b = blockIdx.x;
+   const int ns = spw * C::CONSUMERS;   // stages of the CTA
+
+   G6Ring ring;
+   ring.stage = (char*)g6_smem + (size_t)warp * spw * C::STAGE_BYTES;
+   ring.full = s_bar + warp * G6_MAX_SPW;
+   ring.spw = spw;
+   ring.used = 0;
+   for (int x = tid; x < ns * C::STAGE_BYTES / 8; x += C::NT) ((double*)g6_smem)[x] = 0.0;   // stale alpha reads must be finite
+   if (tid == 0) {
+      for (int s = 0; s < G6_MAX_WARPS * G6_MAX_SPW; ++s) mbar_init(&s_bar[s], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+   }
+   __syncthreads();
+   double* my_cur = cur_glob + (size_t)b * gs.tstride;
+
+   for (int item = 0; item < n_list; ++item) {
+      const int l = list[item];
+      const int64_t r0 = p.loc_row_off[l];
+      const int R = (int)(p.loc_row_off[l + 1] - r0);
+      const int64_t t0 = p.loc_iso_off[l];
+      const int T = (int)(p.loc_iso_off[l + 1] - t0);
+      const int Tp = g6_tp(T), T2 = 2 * Tp + 16;   // two slots per column + 16 dummy slots (one per bank)
+      double* th2 = (double*)(g6_smem + (size_t)ns * C::STAGE_BYTES);   // [2 Tp]: slot A | slot B
+      double* acc = th2 + T2;                                           // [NC][2 Tp]
+      const int64_t* __restrict__ rp = p.row_ptr + r0;
+      double* my_partial = gs.partial + (size_t)b * gs.tstride;
+      RowRec* rec_l = recs + rec_off[item];
+
+      if (tid < 2) {
+         // split rows over CTAs by non-zeros, boundaries rounded to whole chunks
+         const int64_t base = rp[0], nnz = rp[R] - base;
+         const int64_t target = base + (nnz * (int64_t)(b + tid)) / nb;
+         int lo = 0, hi = R;
+         if (b + tid >= nb) lo = R;
+         else if (b + tid == 0) hi = 0;
+         while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (rp[mid] < target) lo = mid + 1; else hi = mid;
+         }
+         if (b + tid < nb) lo = min(R, (lo + C::CROWS / 2) / C::CROWS * C::CROWS);
+         s_rows[tid] = lo;
+      }
+      for (int x = tid; x < C::CONSUMERS * T2; x += C::NT) acc[x] = 0.0;
+      if (tid < 16) th2[2 * Tp + tid] = 0.0;   // dummy slots read as theta = 0
+      __syncthreads();
+      const int ra = s_rows[0], rb = s_rows[1];
+      const int n_chunk = (rb - ra + C::CROWS - 1) / C::CROWS;
+      const int64_t kbase = rp[0];
+      RowRec* rec_cta = rec_l + ra;
+      double* my_acc = acc + (size_t)warp * T2;
+      // sum of a column's two slots over the warp-private accumulators (fixed order), accumulators cleared
+      auto fold = [&](int j) {
+         const int sb = g6_slot_b(j, Tp);
+         double sj = 0.0;
+         for (int w = 0; w < C::CONSUMERS; ++w) {
+            double* aw = acc + (size_t)w * T2;
+            sj += aw[j] + aw[sb];
+            aw[j] = 0.0;
+            aw[sb] = 0.0;
+         }
+         return sj;
+      };
+
+      // ---- setup pass
+      long long tot = 0, kept = 0;
+      int zero = 0;
+      g6_pass<C, true>(p, col16, rec_cta, rp + ra, kbase, r0 + ra, rb - ra, n_chunk, ring, 2 * Tp, th2, my_acc, tot, kept, zero);
+      tot = warp_sum_ll(tot);
+      kept = warp_sum_ll(kept);
+      if (lane == 0 && (tot | kept)) {
+         atomicAdd((unsigned long long*)&gs.ctr[2 * item], (unsigned long long)tot);
+         atomicAdd((unsigned long long*)&gs.ctr[2 * item + 1], (unsigned long long)kept);
+      }
+      __threadfence();
+      asm volatile("fence.proxy.async;" ::: "memory");
+      __syncthreads();
+      for (int j = tid; j < T; j += C::NT) my_partial[j] = fold(j);
+      grid.sync();
+      for (int j = b * (C::NT / 32) + warp; j < T; j += nb * (C::NT / 32)) {
+         double sj = 0.0;
+         for (int cta = lane; cta < nb; cta += 32) sj += __ldcg(gs.partial + (size_t)cta * gs.tstride + j);
+         sj = warp_sum(sj);
+         if (lane == 0) gs.theta_next[j] = sj;
+      }
+      grid.sync();
+      const double total = (double)__ldcg(gs.ctr + 2 * item);
+      const long long kept_all = __ldcg(gs.ctr + 2 * item + 1);
+      const double theta0 = total / (double)T;
+      double* my_sdiv = my_cur + gs.tstride / 2;   // s_j in the upper half of this CTA's theta copy
+      for (int j = tid; j < T; j += C::NT) {
+         my_sdiv[j] = __ldcg(gs.theta_next + j);
+         my_cur[j] = theta0;
+         th2[j] = theta0;
+         th2[g6_slot_b(j, Tp)] = theta0;
+      }
+      grid.sync();   // theta_next is rewritten in iteration 0 only after everyone copied s_j out
+
+      const double tol2 = p.tol * p.tol;
+      int status = LOCUS_ITER_CAP, iters = 0;
+      if (kept_all == 0) {
+         status = LOCUS_NO_ROWS;
+      } else {
+         for (int it = 0; it < p.max_iter; ++it) {
+            iters = it + 1;
+            zero = 0;
+            long long d0 = 0, d1 = 0;
+            g6_pass<C, false>(p, col16, rec_cta, rp + ra, kbase, r0 + ra, rb - ra, n_chunk, ring, 2 * Tp, th2, my_acc, d0, d1, zero);
+            zero = __syncthreads_or(zero);
+            if (zero && tid == 0) atomicOr(&gs.zero_flag[item], 1);
+            for (int j = tid; j < T; j += C::NT) my_partial[j] = fold(j);
+            grid.sync();
+            for (int j = b * (C::NT / 32) + warp; j < T; j += nb * (C::NT / 32)) {
+               double sj = 0.0;
+               for (int cta = lane; cta < nb; cta += 32) sj += __ldcg(gs.partial + (size_t)cta * gs.tstride + j);
+               sj = warp_sum(sj);
+               if (lane == 0) gs.theta_next[j] = sj;
+            }
+            grid.sync();
+            const int zf = *(volatile int*)&gs.zero_flag[item];
+            double d2 = 0.0;
+            for (int j = tid; j < T; j += C::NT) {
+               const double nj = __ldcg(gs.theta_next + j);
+               const double diff = nj - my_cur[j];
+               d2 += diff * diff;
+               th2[j] = nj;
+            }
+            d2 = block_sum<C::NT>(d2, red);
+            if (zf) { status = LOCUS_ZERO_DENOM; break; }
+            if (d2 < tol2) { status = LOCUS_OK; break; }
+            for (int j = tid; j < T; j += C::NT) {
+               const double nj = th2[j];
+               my_cur[j] = nj;
+               const double sj = my_sdiv[j];
+               const double sc = (sj != 0) ? nj / sj : 0.0;
+               th2[j] = sc;
+               th2[g6_slot_b(j, Tp)] = sc;
+            }
+            __syncthreads();
+         }
+      }
+
+      // ---- outputs + epilogue by CTA 0 (src/estimate.cpp:310-356)
+      if (b == 0) {
+         const bool uniform = status == LOCUS_ZERO_DENOM || status == LOCUS_NO_ROWS;
+         double fsum = 0.0;
+         for (int j = tid; j < T; j += C::NT) {
+            const double tj = uniform ? theta0 : my_cur[j];
+            bool na = false;
+            double f = 0.0;
+            if (status != LOCUS_NO_ROWS) f = iso_fpkm(p, tj, p.iso_len[t0 + j], na);
+            p.theta[t0 + j] = tj;
+            p.fpkm[t0 + j] = f;
+            th2[j] = na ? -1.0 : 0.0;
+            fsum += f;
+         }
+         fsum = block_sum<C::NT>(fsum, red);
+         double ksum = 0.0;
+         for (int j = tid; j < T; j += C::NT) {
+            const bool na = th2[j] < 0;
+            const double f = p.fpkm[t0 + j];
+            double fr = 0.0;
+            int kp = 0;
+            if (status != LOCUS_NO_ROWS) {
+               if (!na) fr = f / fsum;
+               kp = !(fr < p.min_frac) ? (na ? -1 : 1) : 0;
+            }
+            p.frac[t0 + j] = fr;
+            p.keep[t0 + j] = kp;
+            if (kp != 0) ksum += f;
+         }
+         ksum = block_sum<C::NT>(ksum, red);
+         if (tid == 0) {
+            p.iters[l] = iters;
+            p.status[l] = status;
+            p.locus_fpkm[l] = ksum;
+         }
+      }
+      grid.sync();   // scratch (partial, theta_next) is reused by the next locus
+   }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+// The kernel pays off with 12 warps per SM (it is bound by instruction latency, not by the shared-memory pipe any more);
+// with fewer the TMA ring kernel (20 warps) is faster. 12 warps fit up to T ~ 800.
+inline bool grid_dual_supports_iso(int T) { return T <= G6_MAX_ISO && G6Cfg<12>::fits(T, 1); }
+inline bool grid_dual_possible(int T) { return T <= G6_MAX_ISO && G6Cfg<4>::fits(T, 1); }   // SBQ_GRID_DUAL=1 forces the kernel wherever it can run
+
+struct GridDualBufs {
+   void** scratch; size_t* scratch_cap;      // partial / theta copies / counters
+   void** col16; size_t* col16_cap;          // u16 slots of the whole batch
+   void** recs; size_t* recs_cap;            // per-locus record offsets (int64, at the front) + row records of the giant loci
+};
+
+template <typename C>
+inline int grid_dual_launch_cfg(const DevParams& dp, const int32_t* d_list, int n_list, int max_iso, const cudaDeviceProp& prop, const GridDualBufs& bf,
+                                const int64_t* d_rec_off, RowRec* d_recs, cudaStream_t st, int* n_launch) {
+   const int spw = C::stages_per_warp(max_iso);
+   const size_t smem = (size_t)spw * C::CONSUMERS * C::STAGE_BYTES + C::fixed_bytes(max_iso);
+   auto kernel = em_grid_dual_kernel<C>;
+   if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -3;
+   int per_sm = 0;
+   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, C::NT, smem) != cudaSuccess || per_sm < 1) return -3;
+   const int nb = prop.multiProcessorCount;
+   const int tstride = 2 * (((max_iso + 255) / 256) * 256);   // theta copy in the lower half, s_j in the upper half
+   const size_t need = ((size_t)nb * tstride * 2 + tstride) * sizeof(double) + (size_t)n_list * (2 * sizeof(long long) + sizeof(int)) + 1024;
+   if (need > *bf.scratch_cap) {
+      if (*bf.scratch) cudaFree(*bf.scratch);
+      *bf.scratch = nullptr;
+      *bf.scratch_cap = 0;
+      if (cudaMalloc(bf.scratch, need) != cudaSuccess) return -4;
+      *bf.scratch_cap = need;
+   }
+   GridScratch gs;
+   char* q = (char*)*bf.scratch;
+   gs.partial = (double*)q; q += (size_t)nb * tstride * sizeof(double);
+   double* cur_glob = (double*)q; q += (size_t)nb * tstride * sizeof(double);
+   gs.theta_next = (double*)q; q += (size_t)tstride * sizeof(double);
+   gs.ctr = (long long*)q; q += (size_t)n_list * 2 * sizeof(long long);
+   gs.zero_flag = (int*)q;
+   gs.tstride = tstride;
+   if (cudaMemsetAsync(gs.ctr, 0, (size_t)n_list * (2 * sizeof(long long) + sizeof(int)), st) != cudaSuccess) return -3;
+   DevParams dpc = dp;
+   const unsigned short* c16 = (const unsigned short*)*bf.col16;
+   int ns_arg = spw;
+   void* args[] = {(void*)&dpc, (void*)&c16, (void*)&d_recs, (void*)&d_rec_off, (void*)&d_list, (void*)&n_list, (void*)&gs, (void*)&cur_glob, (void*)&ns_arg};
+   if (cudaLaunchCooperativeKernel((void*)kernel, dim3(nb), dim3(C::NT), args, smem, st) != cudaSuccess) return -3;
+   ++*n_launch;
+   return 0;
+}
+
+// h_rec_off: n_list + 1 record offsets (host; a locus of R rows owns R + 1 records). prepared: the sorted layout of this upload is already in place.
+inline int grid_dual_launch(const DevParams& dp, int64_t nnz_total, const int32_t* d_list, int n_list, int max_iso, const int64_t* h_rec_off,
+                            const cudaDeviceProp& prop, const GridDualBufs& bf, bool prepared, cudaStream_t st, int* n_launch) {
+   *n_launch = 0;
+   if (n_list == 0) return 0;
+   const size_t need16 = (size_t)nnz_total * 2 + 256;
+   if (need16 > *bf.col16_cap) {
+      if (*bf.col16) cudaFree(*bf.col16);
+      *bf.col16 = nullptr;
+      *bf.col16_cap = 0;
+      if (cudaMalloc(bf.col16, need16) != cudaSuccess) return -4;
+      *bf.col16_cap = need16;
+      prepared = false;
+   }
+   const size_t off_bytes = (((size_t)(n_list + 1) * sizeof(int64_t) + 255) / 256) * 256;
+   const size_t need_rec = off_bytes + (size_t)(h_rec_off[n_list] + 64) * sizeof(RowRec);
+   if (need_rec > *bf.recs_cap) {
+      if (*bf.recs) cudaFree(*bf.recs);
+      *bf.recs = nullptr;
+      *bf.recs_cap = 0;
+      if (cudaMalloc(bf.recs, need_rec) != cudaSuccess) return -4;
+      *bf.recs_cap = need_rec;
+      prepared = false;
+   }
+   const int64_t* d_rec_off = (const int64_t*)*bf.recs;
+   RowRec* d_recs = (RowRec*)((char*)*bf.recs + off_bytes);
+   if (!prepared) {
+      if (cudaMemcpyAsync(*bf.recs, h_rec_off, (size_t)(n_list + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st) != cudaSuccess) return -3;
+      dual_prepare_kernel<<<prop.multiProcessorCount * 8, 256, 0, st>>>(dp, d_list, n_list, d_rec_off, d_recs, (unsigned short*)*bf.col16);
+      ++*n_launch;
+   }
+   const char* env_nc = getenv("SBQ_DUAL_NC");   // tuning: force the number of warps
+   const int force_nc = env_nc ? atoi(env_nc) : 0;
+#define SBQ_TRY6(NC, SPW_MIN)                                                                                                             \
+   if (force_nc ? (force_nc == NC && G6Cfg<NC>::fits(max_iso, 1)) : G6Cfg<NC>::fits(max_iso, SPW_MIN))                                    \
+      return grid_dual_launch_cfg<G6Cfg<NC>>(dp, d_list, n_list, max_iso, prop, bf, d_rec_off, d_recs, st, n_launch);
+   SBQ_TRY6(12, 1)
+   SBQ_TRY6(10, 1)
+   SBQ_TRY6(8, 1)
+   SBQ_TRY6(6, 1)
+   SBQ_TRY6(4, 1)
+#undef SBQ_TRY6
+   return -6;
+}
+
+}  // namespace sbq

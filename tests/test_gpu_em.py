@@ -236,6 +236,47 @@ def test_grid_tier_dense_rows_take_the_oversize_chunk_path(q, oracle_mod):
     qq.close()
 
 
+def _two_slot_edge_locus(R, T, seed):
+    """A giant-tier locus for the two-slot layout (sbq_grid_dual.cuh): Poisson(40) rows plus empty rows, rows dropped by
+    the row filter, rows too long for the sorted layout (walked from global memory), a run of 90-entry rows and a run of
+    60-entry rows (chunks fuller than a ring stage), zero counts."""
+    rng = np.random.default_rng(seed)
+    k = 1 + rng.poisson(40.0, R)
+    k[rng.random(R) < 0.01] = 0
+    long_rows = rng.choice(R, max(2, R // 400), replace=False)
+    k[long_rows] = rng.integers(150, 400, long_rows.size)
+    burst = min(R - 50, R // 2)
+    k[burst:burst + 24] = 90
+    k[burst + 24:burst + 48] = 60
+    k = np.minimum(k, T)
+    row_ptr = np.zeros(R + 1, np.int64)
+    np.cumsum(k, out=row_ptr[1:])
+    col = np.concatenate([np.sort(rng.choice(T, kk, replace=False)) for kk in k]).astype(np.int32)
+    alpha = 10.0 ** rng.uniform(-4.0, -1.5, int(row_ptr[-1]))
+    for i in rng.choice(R, max(1, R // 100), replace=False):
+        alpha[row_ptr[i]:row_ptr[i + 1]] = 5e-6
+    count = rng.integers(0, 4, R).astype(np.int32)
+    return dict(loc_row_off=np.array([0, R], np.int64), loc_iso_off=np.array([0, T], np.int64), row_ptr=row_ptr, col=col, alpha=alpha,
+                count=count, iso_len=rng.integers(400, 8001, T).astype(np.int32), total_mapped_reads=int(count.sum()), meta={})
+
+
+def test_grid_tier_two_slot_layout_edge_shapes(q, oracle_mod, monkeypatch):
+    """Grid tier through the bank-aligned two-slot kernel: ragged row counts (not a multiple of the 8-row chunk), empty /
+    dropped / over-long rows, over-full chunks, a 90-isoform locus (fewer than 16 banks per row in use), and a plain
+    giant-shaped locus; bit-reproducible when the resident batch is solved again."""
+    b = synth.concat([_two_slot_edge_locus(9001, 733, 11), synth.giant(n_loci=1, rows_per_locus=4503, seed=4), _two_slot_edge_locus(3001, 90, 12)])
+    ora = oracle_mod.quantify_batch(b, b["total_mapped_reads"], n_threads=2)
+    monkeypatch.setenv("SBQ_GRID_DUAL", "1")   # read by the planner when the batch is submitted
+    res = run_gpu(q, b, 3, 0)
+    assert res["stats"]["loci_grid"] == 3
+    assert_matches_oracle(res, ora, b, "two-slot grid kernel")
+    q.solve(b["total_mapped_reads"])
+    q.finalize_tpm(q.fpkm_sum())
+    q.download()
+    again = q.results()
+    assert np.array_equal(res["theta"], again["theta"]) and np.array_equal(res["iters"], again["iters"])
+
+
 def _shape_locus(rng, T, R, k_mean, empty_rows=0, dropped_rows=0):
     """One locus with Poisson(k_mean) columns per row (clamped to 1..T), plus rows without entries and rows whose
     alphas are all below the row filter."""
