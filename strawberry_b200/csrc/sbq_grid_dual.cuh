@@ -9,7 +9,7 @@
 //    slot B(j) = Tp + 16*(j/16) + ((j + j/16) mod 16) (the column's 16-block rotated by the block index: a different
 //    bank). Every non-zero may use either slot of its column, which turns "48 balls into 16 bins" into a two-choice
 //    allocation: the fullest bank drops from ~7 to ~3.85 entries.
-//  * dual_prepare_kernel (once per upload, one warp per row) picks the slot of every non-zero (greedy least-loaded
+//  * dual_prepare_kernel (once per upload; a warp stages 32 rows, every lane allocates one row, the warp permutes) picks the slot of every non-zero (greedy least-loaded
 //    bank + two improvement sweeps) and re-sorts the row IN PLACE inside its CSR range into a jagged-diagonal order:
 //    step-major, within a step one entry per bank, banks ranked by load. Lane x of a half-warp then only ever touches
 //    bank rank x: the alpha / column reads are contiguous and the theta gather and the accumulator update are
@@ -81,18 +81,26 @@ struct G6Cfg {
 };
 
 // ------------------------------------------------------------------------------------------------------------------
-// prepare: one warp per row
+// prepare: a warp takes 32 consecutive rows. The rows' bank pairs are staged in shared memory by the whole warp, then
+// every LANE runs the (sequential) two-choice allocation of one row, then the whole warp permutes the rows in place.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int G6_PREP_WARPS = 8;
+constexpr int G6_PSTRIDE = G6_MAXROW + 1;   // odd byte stride between the rows of a tile
+
+struct G6PrepTile {
+   unsigned char bank_a[32][G6_PSTRIDE];   // bank of slot A per entry; overwritten by (destination | slot choice << 7)
+   unsigned char bank_b[32][G6_PSTRIDE];
+   unsigned char load[16][32], fill[16][32], pos[16][32];   // per-lane scratch, [bank][lane]: conflict-free
+   unsigned char pre[G6_LMAX + 1][32];
+   unsigned char cnt[32][8];               // record bytes of the 32 rows
+};
+
+__global__ void __launch_bounds__(G6_PREP_WARPS * 32)
 dual_prepare_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, const int64_t* __restrict__ rec_off, RowRec* __restrict__ recs,
                     unsigned short* __restrict__ col16) {
-   struct Scratch {
-      unsigned char bank_a[G6_MAXROW], bank_b[G6_MAXROW], pick[G6_MAXROW], seq[G6_MAXROW];
-      int load[16], pos[16], pre[G6_LMAX + 1], ok;
-   };
-   __shared__ Scratch sc_all[8];
+   extern __shared__ __align__(16) unsigned char g6_prep_smem[];
    const int lane = threadIdx.x & 31;
-   Scratch& sc = sc_all[threadIdx.x >> 5];
+   G6PrepTile& tl = reinterpret_cast<G6PrepTile*>(g6_prep_smem)[threadIdx.x >> 5];
    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
    double* alpha = const_cast<double*>(p.alpha);
    for (int item = 0; item < n_list; ++item) {
@@ -108,104 +116,118 @@ dual_prepare_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, c
          rec_l[R].cnt[lane] = 0;
          if (lane == 0) { rec_l[R].neff = -1; rec_l[R].koff = (uint32_t)(rp[R] - kbase); }
       }
-      for (int64_t row = wid; row < R; row += nw) {
-         const int64_t k0 = rp[row], k1 = rp[row + 1];
-         RowRec* rec = rec_l + row;
-         const int64_t n64 = k1 - k0;
-         bool sorted = n64 <= G6_MAXROW;
-         double a[3];
-         int c[3];
+      for (int64_t tile0 = wid * 32; tile0 < R; tile0 += nw * 32) {
+         const int nrow = (int)min((int64_t)32, R - tile0);
+         // my row (lane-per-row phase): extent and whether it takes the sorted layout at all
+         const int64_t my_k0 = lane < nrow ? rp[tile0 + lane] : 0, my_k1 = lane < nrow ? rp[tile0 + lane + 1] : 0;
+         const int my_n = (int)min((int64_t)(G6_MAXROW + 1), my_k1 - my_k0);
+         // phase A: stage the bank pairs of the 32 rows
+         for (int r = 0; r < nrow; ++r) {
+            const int64_t k0 = __shfl_sync(0xffffffffu, my_k0, r);
+            const int n = __shfl_sync(0xffffffffu, my_n, r);
+            if (n > G6_MAXROW) continue;
+            for (int idx = lane; idx < n; idx += 32) {
+               const int c = p.col[k0 + idx];
+               tl.bank_a[r][idx] = (unsigned char)(c & 15);
+               tl.bank_b[r][idx] = (unsigned char)((c + (c >> 4)) & 15);
+            }
+         }
+         __syncwarp();
+         // phase B: lane = row. Two-choice allocation: greedy least-loaded bank, then two sweeps that move an entry to its
+         // other bank when that lowers the larger of the two loads.
+         bool sorted = lane < nrow && my_n <= G6_MAXROW;
          if (sorted) {
-            const int n = (int)n64;
+            const int n = my_n;
+#pragma unroll
+            for (int b = 0; b < 16; ++b) tl.load[b][lane] = 0;
+            unsigned pick[3] = {0u, 0u, 0u};   // bit e: entry e uses slot B
+            for (int e = 0; e < n; ++e) {
+               const int ba = tl.bank_a[lane][e], bb = tl.bank_b[lane][e];
+               const bool pk = tl.load[bb][lane] < tl.load[ba][lane];
+               if (pk) pick[e >> 5] |= 1u << (e & 31);
+               ++tl.load[pk ? bb : ba][lane];
+            }
+            for (int sweep = 0; sweep < 2; ++sweep) {
+               for (int e = 0; e < n; ++e) {
+                  const int ba = tl.bank_a[lane][e], bb = tl.bank_b[lane][e];
+                  const bool pk = (pick[e >> 5] >> (e & 31)) & 1u;
+                  const int cur = pk ? bb : ba, alt = pk ? ba : bb;
+                  if (tl.load[cur][lane] > tl.load[alt][lane] + 1) {
+                     --tl.load[cur][lane];
+                     ++tl.load[alt][lane];
+                     pick[e >> 5] ^= 1u << (e & 31);
+                  }
+               }
+            }
+            int L = 0;
+#pragma unroll
+            for (int b = 0; b < 16; ++b) L = max(L, (int)tl.load[b][lane]);
+            sorted = L <= G6_LMAX;
+            if (sorted) {
+               // banks ranked by (load desc, bank asc) -> lane position; per-step entry counts and their prefix
+               for (int b = 0; b < 16; ++b) {
+                  const int lb = tl.load[b][lane];
+                  int ps = 0;
+#pragma unroll
+                  for (int y = 0; y < 16; ++y) { const int ly = tl.load[y][lane]; ps += (ly > lb) || (ly == lb && y < b); }
+                  tl.pos[b][lane] = (unsigned char)ps;
+                  tl.fill[b][lane] = 0;
+               }
+               int acc = 0, steps = 0;
+               for (int s = 0; s <= G6_LMAX; ++s) {
+                  tl.pre[s][lane] = (unsigned char)acc;
+                  int cn = 0;
+#pragma unroll
+                  for (int b = 0; b < 16; ++b) cn += tl.load[b][lane] > s;
+                  if (s < G6_LMAX) { tl.cnt[lane][s] = (unsigned char)cn; steps += cn > 0; }
+                  acc += cn;
+               }
+               tl.cnt[lane][6] = 0;
+               tl.cnt[lane][7] = (unsigned char)steps;
+               for (int e = 0; e < n; ++e) {
+                  const bool pk = (pick[e >> 5] >> (e & 31)) & 1u;
+                  const int bk = pk ? tl.bank_b[lane][e] : tl.bank_a[lane][e];
+                  const int sq = tl.fill[bk][lane]++;
+                  tl.bank_a[lane][e] = (unsigned char)((tl.pre[sq][lane] + tl.pos[bk][lane]) | (pk ? 0x80 : 0));
+               }
+            }
+         }
+         if (lane < nrow && !sorted) {
+#pragma unroll
+            for (int s = 0; s < 8; ++s) tl.cnt[lane][s] = s == 0 ? G6_FLAG : 0;
+         }
+         __syncwarp();
+         // phase C: permute the rows in place (alpha) and write slots and records
+         for (int r = 0; r < nrow; ++r) {
+            const int64_t k0 = __shfl_sync(0xffffffffu, my_k0, r), k1 = __shfl_sync(0xffffffffu, my_k1, r);
+            const bool srt = __shfl_sync(0xffffffffu, (int)sorted, r);
+            RowRec* rec = rec_l + tile0 + r;
+            if (lane < 8) rec->cnt[lane] = tl.cnt[r][lane];
+            if (lane == 0) { rec->neff = -1; rec->koff = (uint32_t)(k0 - kbase); }
+            if (!srt) {   // left in CSR order with plain (slot A) columns; the EM kernel walks it from global memory
+               for (int64_t k = k0 + lane; k < k1; k += 32) col16[k] = (unsigned short)p.col[k];
+               continue;
+            }
+            const int n = (int)(k1 - k0);
+            double a[3];
+            int c[3];
 #pragma unroll
             for (int m = 0; m < 3; ++m) {
                const int idx = lane + 32 * m;
-               const bool v = idx < n;
-               a[m] = v ? alpha[k0 + idx] : 0.0;
-               c[m] = v ? p.col[k0 + idx] : 0;
-               if (v) {
-                  sc.bank_a[idx] = (unsigned char)(c[m] & 15);
-                  sc.bank_b[idx] = (unsigned char)((c[m] + (c[m] >> 4)) & 15);
+               a[m] = idx < n ? alpha[k0 + idx] : 0.0;
+               c[m] = idx < n ? p.col[k0 + idx] : 0;
+            }
+            __syncwarp();   // the row is in registers before any of it is overwritten
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+               const int idx = lane + 32 * m;
+               if (idx < n) {
+                  const unsigned d = tl.bank_a[r][idx];
+                  alpha[k0 + (d & 0x7fu)] = a[m];
+                  col16[k0 + (d & 0x7fu)] = (unsigned short)((d & 0x80u) ? g6_slot_b(c[m], Tp) : c[m]);
                }
             }
-            if (lane < 16) sc.load[lane] = 0;
-            __syncwarp();
-            if (lane == 0) {
-               // two-choice allocation: greedy least-loaded bank, then two sweeps that move an entry to its other bank when
-               // that lowers the larger of the two loads
-               for (int e = 0; e < n; ++e) {
-                  const int ba = sc.bank_a[e], bb = sc.bank_b[e];
-                  const int pk = sc.load[bb] < sc.load[ba];
-                  sc.pick[e] = (unsigned char)pk;
-                  ++sc.load[pk ? bb : ba];
-               }
-               for (int sweep = 0; sweep < 2; ++sweep) {
-                  for (int e = 0; e < n; ++e) {
-                     const int ba = sc.bank_a[e], bb = sc.bank_b[e];
-                     const int cur = sc.pick[e] ? bb : ba, alt = sc.pick[e] ? ba : bb;
-                     if (sc.load[cur] > sc.load[alt] + 1) { --sc.load[cur]; ++sc.load[alt]; sc.pick[e] ^= 1; }
-                  }
-               }
-               int L = 0;
-               for (int b = 0; b < 16; ++b) L = max(L, sc.load[b]);
-               sc.ok = L <= G6_LMAX;
-               if (sc.ok) {
-                  // banks ranked by (load desc, bank asc) -> lane position; per-step entry counts and their prefix
-                  for (int b = 0; b < 16; ++b) {
-                     int ps = 0;
-                     for (int y = 0; y < 16; ++y) ps += (sc.load[y] > sc.load[b]) || (sc.load[y] == sc.load[b] && y < b);
-                     sc.pos[b] = ps;
-                  }
-                  int acc = 0;
-                  for (int s = 0; s <= G6_LMAX; ++s) {
-                     sc.pre[s] = acc;
-                     int cn = 0;
-                     for (int b = 0; b < 16; ++b) cn += sc.load[b] > s;
-                     acc += cn;
-                  }
-                  int fill[16];
-#pragma unroll
-                  for (int b = 0; b < 16; ++b) fill[b] = 0;
-                  for (int e = 0; e < n; ++e) {
-                     const int bk = sc.pick[e] ? sc.bank_b[e] : sc.bank_a[e];
-                     int sq = 0;
-#pragma unroll
-                     for (int b = 0; b < 16; ++b)
-                        if (b == bk) sq = fill[b]++;
-                     sc.seq[e] = (unsigned char)sq;
-                  }
-               }
-            }
-            __syncwarp();
-            sorted = sc.ok != 0;
          }
-         if (!sorted) {
-            // left in CSR order with plain (slot A) columns; the EM kernel walks it from global memory
-            for (int64_t k = k0 + lane; k < k1; k += 32) col16[k] = (unsigned short)p.col[k];
-            if (lane < 8) rec->cnt[lane] = lane == 0 ? G6_FLAG : 0;
-            if (lane == 0) { rec->neff = -1; rec->koff = (uint32_t)(k0 - kbase); }
-            __syncwarp();
-            continue;
-         }
-         const int n = (int)n64;
-#pragma unroll
-         for (int m = 0; m < 3; ++m) {
-            const int idx = lane + 32 * m;
-            if (idx < n) {
-               const int pk = sc.pick[idx];
-               const int bk = pk ? sc.bank_b[idx] : sc.bank_a[idx];
-               const int dest = sc.pre[sc.seq[idx]] + sc.pos[bk];
-               alpha[k0 + dest] = a[m];
-               col16[k0 + dest] = (unsigned short)(pk ? g6_slot_b(c[m], Tp) : c[m]);
-            }
-         }
-         if (lane < 8) {
-            int v = 0;
-            if (lane < G6_LMAX) v = sc.pre[lane + 1] - sc.pre[lane];
-            else if (lane == 7) { for (int s = 0; s < G6_LMAX; ++s) v += sc.pre[s + 1] > sc.pre[s]; }
-            rec->cnt[lane] = (unsigned char)v;
-         }
-         if (lane == 0) { rec->neff = -1; rec->koff = (uint32_t)(k0 - kbase); }
          __syncwarp();
       }
    }
@@ -731,7 +753,9 @@ inline int grid_dual_launch(const DevParams& dp, int64_t nnz_total, const int32_
    RowRec* d_recs = (RowRec*)((char*)*bf.recs + off_bytes);
    if (!prepared) {
       if (cudaMemcpyAsync(*bf.recs, h_rec_off, (size_t)(n_list + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st) != cudaSuccess) return -3;
-      dual_prepare_kernel<<<prop.multiProcessorCount * 8, 256, 0, st>>>(dp, d_list, n_list, d_rec_off, d_recs, (unsigned short*)*bf.col16);
+      const size_t psmem = (size_t)G6_PREP_WARPS * sizeof(G6PrepTile);
+      if (cudaFuncSetAttribute(dual_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem) != cudaSuccess) return -3;
+      dual_prepare_kernel<<<prop.multiProcessorCount * 2, G6_PREP_WARPS * 32, psmem, st>>>(dp, d_list, n_list, d_rec_off, d_recs, (unsigned short*)*bf.col16);
       ++*n_launch;
    }
    const char* env_nc = getenv("SBQ_DUAL_NC");   // tuning: force the number of warps
