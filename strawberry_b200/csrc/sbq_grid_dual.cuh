@@ -294,18 +294,19 @@ __device__ __forceinline__ void g6_turn_steps(const DevParams& p, const double* 
    const bool is_lo = lane < 16;
    double pr[G6_NR][LS];          // alpha (SETUP) or alpha * theta
    unsigned so[G6_NR][LS];        // slot * 8: byte offset into theta (th2) and into the accumulator row (my)
+   // (step-major loops: consecutive instructions belong to different rows, i.e. to independent dependency chains)
+   int dummy[G6_NR];
 #pragma unroll
-   for (int q = 0; q < G6_NR; ++q) {
-      int dummy = dummy0;
+   for (int e = 0; e < LS; ++e) {
 #pragma unroll
-      for (int e = 0; e < LS; ++e) {
+      for (int q = 0; q < G6_NR; ++q) {
          const unsigned ce = ((e < 4 ? cw0[q] : cw1[q]) >> (8 * (e & 3))) & 0xffu;
          const bool valid = (unsigned)x < ce;
          const double a = a_s[kk[q]];
          const int c = (int)c_s[kk[q]];
-         if (e == 0) dummy = dummy0 + (valid ? (c & 15) : x);   // a lane without any entry in the row: a bank of its own choice (rare extra wavefront)
+         if (e == 0) dummy[q] = dummy0 + (valid ? (c & 15) : x);   // a lane without any entry in the row: a bank of its own choice (rare extra wavefront)
          pr[q][e] = (SETUP && !valid) ? 0.0 : a;   // EM: a lane without an entry reads a finite stale alpha and multiplies it by theta[dummy] = 0
-         so[q][e] = (unsigned)(valid ? c : dummy) << 3;
+         so[q][e] = (unsigned)(valid ? c : dummy[q]) << 3;
          kk[q] += ce;
       }
    }
@@ -336,23 +337,40 @@ __device__ __forceinline__ void g6_turn_steps(const DevParams& p, const double* 
    } else {
       double d[G6_NR];
 #pragma unroll
-      for (int q = 0; q < G6_NR; ++q) {
-         d[q] = 0.0;
+      for (int q = 0; q < G6_NR; ++q) d[q] = 0.0;
 #pragma unroll
-         for (int e = 0; e < LS; ++e) {
+      for (int e = 0; e < LS; ++e) {
+#pragma unroll
+         for (int q = 0; q < G6_NR; ++q) {
             pr[q][e] *= *reinterpret_cast<const double*>(th2b + so[q][e]);
             d[q] += pr[q][e];
          }
       }
 #pragma unroll
-      for (int q = 0; q < G6_NR; ++q) d[q] = g6_half_sum(d[q]);
+      for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+         for (int q = 0; q < G6_NR; ++q) d[q] += __shfl_xor_sync(0xffffffffu, d[q], o);
+      }
+      // r_q = n_q / d_q, four independent straight-line divisions; denominators outside the fast path's range (never seen on
+      // real data) take the IEEE division afterwards
+      bool odd = false;
+      double dd[G6_NR];
 #pragma unroll
       for (int q = 0; q < G6_NR; ++q) {
-         r[q] = 0.0;
-         if (ne[q] >= 0) {
-            if (d[q] == 0) zero = 1;
-            else r[q] = (d[q] > 1e-290 && d[q] < 1e290) ? fast_div_pos((double)ne[q], d[q]) : (double)ne[q] / d[q];
-         }
+         const bool live = ne[q] >= 0;
+         const bool safe = d[q] > 1e-290 && d[q] < 1e290;
+         if (live && d[q] == 0) zero = 1;
+         odd |= live && d[q] != 0 && !safe;
+         dd[q] = safe ? d[q] : 1.0;
+      }
+#pragma unroll
+      for (int q = 0; q < G6_NR; ++q) r[q] = fast_div_pos((double)max(ne[q], 0), dd[q]);
+#pragma unroll
+      for (int q = 0; q < G6_NR; ++q) r[q] = (ne[q] >= 0 && d[q] > 1e-290 && d[q] < 1e290) ? r[q] : 0.0;
+      if (odd) {
+#pragma unroll
+         for (int q = 0; q < G6_NR; ++q)
+            if (ne[q] >= 0 && d[q] != 0 && !(d[q] > 1e-290 && d[q] < 1e290)) r[q] = (double)ne[q] / d[q];
       }
    }
    // M-phase: rows in order (two rows of a half-warp may share a column), inside a row the low half-warp first. A row's
