@@ -240,7 +240,8 @@ struct G6Ring {      // the private ring of one warp
    char* stage;      // spw stages
    uint64_t* full;   // [spw]
    int spw;
-   unsigned used;    // chunks this warp has consumed so far (all passes): stage = used % spw, parity = (used / spw) & 1
+   int next;         // stage of the next chunk this warp consumes
+   unsigned phase;   // bit s: parity the next wait on stage s expects
 };
 
 __device__ __forceinline__ double g6_half_sum(double v) {   // sum over the 16 lanes of a half-warp
@@ -449,24 +450,26 @@ __device__ __forceinline__ void g6_pass(const DevParams& p, const unsigned short
    // prologue: fill the ring (records written with ordinary global stores in the setup pass are read by bulk copies)
    asm volatile("fence.proxy.async;" ::: "memory");
    if (lane == 0) {
+      int sx = ring.next;
       for (int i = 0; i < min(ring.spw, n_mine); ++i) {
          const int c = warp + i * C::CONSUMERS;
-         const unsigned u = ring.used + (unsigned)i;
          g6_issue<C>(p, col16, rec_cta, n_rows, c, rp_cta[min(c * C::CROWS, n_rows)], rp_cta[min((c + 1) * C::CROWS, n_rows)],
-                     ring.stage + (size_t)(u % (unsigned)ring.spw) * C::STAGE_BYTES, &ring.full[u % (unsigned)ring.spw]);
+                     ring.stage + (size_t)sx * C::STAGE_BYTES, &ring.full[sx]);
+         sx = sx + 1 == ring.spw ? 0 : sx + 1;
       }
    }
    __syncwarp();
    for (int i = 0; i < n_mine; ++i) {
       const int c = warp + i * C::CONSUMERS;
-      const unsigned u = ring.used + (unsigned)i;
-      const int sidx = (int)(u % (unsigned)ring.spw);
+      const int sidx = ring.next;
       // boundaries of the chunk that will refill this stage, fetched now so that the loads overlap the turn
       const int cn = c + ring.spw * C::CONSUMERS;
       int64_t kn0 = 0, kn1 = 0;
       if (lane == 0 && cn < n_chunk) { kn0 = rp_cta[min(cn * C::CROWS, n_rows)]; kn1 = rp_cta[min((cn + 1) * C::CROWS, n_rows)]; }
       const int i0 = c * C::CROWS, i1 = min(i0 + C::CROWS, n_rows);       // rows of the chunk (CTA-local)
-      mbar_wait(&ring.full[sidx], (u / (unsigned)ring.spw) & 1u);
+      mbar_wait(&ring.full[sidx], (ring.phase >> sidx) & 1u);
+      ring.phase ^= 1u << sidx;
+      ring.next = sidx + 1 == ring.spw ? 0 : sidx + 1;
       char* st = ring.stage + (size_t)sidx * C::STAGE_BYTES;
       const RowRec* rec_s = (const RowRec*)(st + C::R_OFF);
       const uint32_t ck0 = rec_s[0].koff;
@@ -497,7 +500,6 @@ __device__ __forceinline__ void g6_pass(const DevParams& p, const unsigned short
                                tot, kept, zero);
       }
    }
-   ring.used += (unsigned)n_mine;
 }
 
 template <typename C>
@@ -517,7 +519,8 @@ em_grid_dual_kernel(DevParams p, const unsigned short* __restrict__ col16, RowRe
    ring.stage = (char*)g6_smem + (size_t)warp * spw * C::STAGE_BYTES;
    ring.full = s_bar + warp * G6_MAX_SPW;
    ring.spw = spw;
-   ring.used = 0;
+   ring.next = 0;
+   ring.phase = 0;
    for (int x = tid; x < ns * C::STAGE_BYTES / 8; x += C::NT) ((double*)g6_smem)[x] = 0.0;   // stale alpha reads must be finite
    if (tid == 0) {
       for (int s = 0; s < G6_MAX_WARPS * G6_MAX_SPW; ++s) mbar_init(&s_bar[s], 1);
