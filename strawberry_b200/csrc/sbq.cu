@@ -156,9 +156,9 @@ struct sbq_ctx {
    size_t warp_list_off = 0, grid_list_off = 0;
 
    // device
-   DevBuf d_in, d_out, d_lists, d_grid_scratch, d_col16, d_blk;
-   bool col16_ready = false, grid_tma_ok = false, grid_blk_ok = false;
-   std::vector<int64_t> grid_blk_off;            // row-record offset of every grid-tier locus (+ total), list order
+   DevBuf d_in, d_out, d_lists, d_grid_scratch, d_col16, d_rowrec;
+   bool col16_ready = false, grid_tma_ok = false, grid_dual_ok = false;
+   std::vector<int64_t> grid_rec_off;            // row-record offset of every grid-tier locus (+ total), list order
    int grid_max_iso = 1;
    int grid_variant = 0;                         // which giant-locus kernel the last solve used (sbq_launch_stat.variant)
    DevParams dp{};
@@ -296,7 +296,7 @@ int plan(sbq_ctx* c) {
    c->max_iso_all = 1;
    c->grid_max_iso = 1;
    c->grid_tma_ok = true;
-   c->grid_blk_ok = !getenv("SBQ_GRID_NO_DUAL");   // two-slot layout kernel (sbq_grid_dual.cuh) unless a locus does not qualify
+   c->grid_dual_ok = !getenv("SBQ_GRID_NO_DUAL");   // two-slot layout kernel (sbq_grid_dual.cuh) unless a locus does not qualify
    std::vector<int64_t> nnz_of(c->n_loci);
    LaunchClass* slot[5][4] = {};
    std::vector<LaunchClass> tmp;
@@ -323,7 +323,7 @@ int plan(sbq_ctx* c) {
          c->grid_max_iso = std::max(c->grid_max_iso, (int)T);
          if (!grid_tma_supports((int)T, (long long)R, c->prop.multiProcessorCount)) c->grid_tma_ok = false;
          // bank-aligned two-slot layout: 16-bit slots, 32-bit offsets inside the locus, rows short enough on average
-         if ((!grid_dual_supports_iso((int)T) && !getenv("SBQ_GRID_DUAL")) || !grid_dual_possible((int)T) || nnz >= (1LL << 32) || nnz > 56 * R) c->grid_blk_ok = false;
+         if ((!grid_dual_supports_iso((int)T) && !getenv("SBQ_GRID_DUAL")) || !grid_dual_possible((int)T) || nnz >= (1LL << 32) || nnz > 56 * R) c->grid_dual_ok = false;
       } else {
          int cs = c->force_cluster ? c->force_cluster : cluster_size_for(nnz);
          int csi = cs == 1 ? 0 : cs == 2 ? 1 : cs == 4 ? 2 : cs == 8 ? 3 : 4;
@@ -343,10 +343,10 @@ int plan(sbq_ctx* c) {
    auto by_size = [&](int32_t a, int32_t b) { return nnz_of[a] != nnz_of[b] ? nnz_of[a] > nnz_of[b] : a < b; };
    std::sort(c->warp_list.begin(), c->warp_list.end(), by_size);
    std::sort(c->grid_list.begin(), c->grid_list.end(), by_size);
-   c->grid_blk_off.assign(c->grid_list.size() + 1, 0);
+   c->grid_rec_off.assign(c->grid_list.size() + 1, 0);
    for (size_t i = 0; i < c->grid_list.size(); ++i) {
       const int64_t R = lro[c->grid_list[i] + 1] - lro[c->grid_list[i]];
-      c->grid_blk_off[i + 1] = c->grid_blk_off[i] + R + 1;
+      c->grid_rec_off[i + 1] = c->grid_rec_off[i] + R + 1;
    }
    for (auto& lc : tmp) {
       std::sort(lc.loci.begin(), lc.loci.end(), by_size);
@@ -488,7 +488,7 @@ void sbq_destroy(sbq_ctx* c) {
    c->h_lists.release();
    c->r_theta.release(); c->r_fpkm.release(); c->r_frac.release(); c->r_tpm.release();
    c->r_locus_fpkm.release(); c->r_keep.release(); c->r_iters.release(); c->r_status.release();
-   c->d_in.release(); c->d_out.release(); c->d_lists.release(); c->d_grid_scratch.release(); c->d_col16.release(); c->d_blk.release(); c->d_bias.release();
+   c->d_in.release(); c->d_out.release(); c->d_lists.release(); c->d_grid_scratch.release(); c->d_col16.release(); c->d_rowrec.release(); c->d_bias.release();
    c->h_cov.release(); c->r_beta.release(); c->r_outer.release();
    c->h_wseg.release(); c->h_wn.release(); c->h_wmask.release(); c->h_wpool.release(); c->h_wlen.release(); c->d_weights.release();
    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -803,9 +803,9 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
       CU(cudaEventRecord(c->ev[6], st));
       int n_launch = 0;
       int rc;
-      if (c->grid_blk_ok) {
-         GridDualBufs bf{&c->d_grid_scratch.p, &c->d_grid_scratch.cap, &c->d_col16.p, &c->d_col16.cap, &c->d_blk.p, &c->d_blk.cap};
-         rc = grid_dual_launch(c->dp, c->nnz, c->d_lists_p + c->grid_list_off, (int)c->grid_list.size(), c->grid_max_iso, c->grid_blk_off.data(),
+      if (c->grid_dual_ok) {
+         GridDualBufs bf{&c->d_grid_scratch.p, &c->d_grid_scratch.cap, &c->d_col16.p, &c->d_col16.cap, &c->d_rowrec.p, &c->d_rowrec.cap};
+         rc = grid_dual_launch(c->dp, c->nnz, c->d_lists_p + c->grid_list_off, (int)c->grid_list.size(), c->grid_max_iso, c->grid_rec_off.data(),
                               c->prop, bf, c->col16_ready, st, &n_launch);
          if (rc == 0) c->col16_ready = true;
          c->grid_variant = 3;
