@@ -13,7 +13,7 @@
 //    bank + two improvement sweeps) and re-sorts the row IN PLACE inside its CSR range into a jagged-diagonal order:
 //    step-major, within a step one entry per bank, banks ranked by load. Lane x of a half-warp then only ever touches
 //    bank rank x: the alpha / column reads are contiguous and the theta gather and the accumulator update are
-//    conflict-free. The u16 column copy holds the slot; a 16-byte record per row holds the per-step entry counts, the
+//    conflict-free. The u16 column copy holds the slot as a byte offset (slot * 8); a 16-byte record per row holds the per-step entry counts, the
 //    effective count and the row's offset (it replaces row pointer + count in the stream: same bytes).
 //  * em_grid_dual_kernel: persistent cooperative kernel, one CTA per SM = NC consumer warps + 1 producer warp. The
 //    producer streams 8-row chunks (alpha slab, u16 slab, record slab - three 1-D TMA bulk copies) into an NS-deep
@@ -26,7 +26,7 @@
 //
 // Rows with more than 96 non-zeros or whose fullest bank still holds more than 6 entries keep their CSR order (flag in
 // the record) and are walked by a whole warp from global memory, as are the rows of a chunk fuller than a stage.
-// Eligibility (host planner): T <= 32760, locus non-zeros < 2^32, on average <= 56 non-zeros per row, shared memory for
+// Eligibility (host planner): T <= 4080, locus non-zeros < 2^32, on average <= 56 non-zeros per row, shared memory for
 // at least 3 consumer warps. Anything else runs on em_grid_tma_kernel / em_grid_kernel.
 #pragma once
 #include "sbq_grid_tma.cuh"
@@ -47,7 +47,7 @@ static_assert(sizeof(RowRec) == 16, "one 16-byte unit per row");
 constexpr int G6_NR = 4;                         // rows a half-warp keeps in flight
 constexpr int G6_MAX_SPW = 4;                    // ring stages per warp (at most)
 constexpr int G6_MAX_WARPS = 16;
-constexpr int G6_MAX_ISO = 32760;
+constexpr int G6_MAX_ISO = 4080;                 // slot * 8 must fit the u16 stream: (2 Tp + 16) * 8 <= 65535
 
 __host__ __device__ __forceinline__ int g6_tp(int T) { return (T + 15) & ~15; }
 __host__ __device__ __forceinline__ int g6_slot_b(int j, int Tp) { return Tp + (j & ~15) + ((j + (j >> 4)) & 15); }
@@ -205,7 +205,7 @@ dual_prepare_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, c
             if (lane < 8) rec->cnt[lane] = tl.cnt[r][lane];
             if (lane == 0) { rec->neff = -1; rec->koff = (uint32_t)(k0 - kbase); }
             if (!srt) {   // left in CSR order with plain (slot A) columns; the EM kernel walks it from global memory
-               for (int64_t k = k0 + lane; k < k1; k += 32) col16[k] = (unsigned short)p.col[k];
+               for (int64_t k = k0 + lane; k < k1; k += 32) col16[k] = (unsigned short)(p.col[k] << 3);
                continue;
             }
             const int n = (int)(k1 - k0);
@@ -224,7 +224,7 @@ dual_prepare_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, c
                if (idx < n) {
                   const unsigned d = tl.bank_a[r][idx];
                   alpha[k0 + (d & 0x7fu)] = a[m];
-                  col16[k0 + (d & 0x7fu)] = (unsigned short)((d & 0x80u) ? g6_slot_b(c[m], Tp) : c[m]);
+                  col16[k0 + (d & 0x7fu)] = (unsigned short)(((d & 0x80u) ? g6_slot_b(c[m], Tp) : c[m]) << 3);
                }
             }
          }
@@ -261,18 +261,18 @@ __device__ __forceinline__ void g6_walk_row(const DevParams& p, const unsigned s
       keep = __any_sync(0xffffffffu, keep);
       if (lane == 0) { rec_g->neff = keep ? n_i : -1; *neff_row = keep ? n_i : -1; tot += n_i; kept += keep; }
       if (keep)
-         for (int64_t k = a + lane; k < b; k += 32) my[col16[k]] += p.alpha[k];
+         for (int64_t k = a + lane; k < b; k += 32) my[col16[k] >> 3] += p.alpha[k];
    } else {
       const int ne = rec_g->neff;
       if (ne >= 0) {
          double d = 0.0;
-         for (int64_t k = a + lane; k < b; k += 32) d += p.alpha[k] * th2[col16[k]];
+         for (int64_t k = a + lane; k < b; k += 32) d += p.alpha[k] * th2[col16[k] >> 3];
          d = warp_sum(d);
          if (d == 0) {
             zero = 1;
          } else {
             const double rr = (double)ne / d;
-            for (int64_t k = a + lane; k < b; k += 32) { const int cc = col16[k]; my[cc] += p.alpha[k] * th2[cc] * rr; }
+            for (int64_t k = a + lane; k < b; k += 32) { const int cc = col16[k] >> 3; my[cc] += p.alpha[k] * th2[cc] * rr; }
          }
       }
    }
@@ -294,7 +294,7 @@ __device__ __forceinline__ void g6_turn_steps(const DevParams& p, const double* 
    const int lane = threadIdx.x & 31, x = lane & 15;
    const bool is_lo = lane < 16;
    double pr[G6_NR][LS];          // alpha (SETUP) or alpha * theta
-   unsigned so[G6_NR][LS];        // slot * 8: byte offset into theta (th2) and into the accumulator row (my)
+   unsigned so[G6_NR][LS];        // slot * 8 (as stored in the u16 stream): byte offset into theta (th2) and into the accumulator row (my)
    // (step-major loops: consecutive instructions belong to different rows, i.e. to independent dependency chains)
    int dummy[G6_NR];
 #pragma unroll
@@ -305,9 +305,9 @@ __device__ __forceinline__ void g6_turn_steps(const DevParams& p, const double* 
          const bool valid = (unsigned)x < ce;
          const double a = a_s[kk[q]];
          const int c = (int)c_s[kk[q]];
-         if (e == 0) dummy[q] = dummy0 + (valid ? (c & 15) : x);   // a lane without any entry in the row: a bank of its own choice (rare extra wavefront)
+         if (e == 0) dummy[q] = dummy0 + (valid ? (c & 0x78) : 8 * x);   // a lane without any entry in the row: a bank of its own choice (rare extra wavefront)
          pr[q][e] = (SETUP && !valid) ? 0.0 : a;   // EM: a lane without an entry reads a finite stale alpha and multiplies it by theta[dummy] = 0
-         so[q][e] = (unsigned)(valid ? c : dummy[q]) << 3;
+         so[q][e] = (unsigned)(valid ? c : dummy[q]);
          kk[q] += ce;
       }
    }
@@ -444,7 +444,7 @@ template <typename C, bool SETUP>
 __device__ __forceinline__ void g6_pass(const DevParams& p, const unsigned short* __restrict__ col16, RowRec* __restrict__ rec_cta /* row 0 of this CTA */,
                                         const int64_t* __restrict__ rp_cta /* row pointer of the CTA's row 0 */, const int64_t kbase /* first non-zero of the locus */,
                                         int64_t row_abs0 /* absolute row of the CTA's row 0 */, int n_rows, int n_chunk, G6Ring& ring,
-                                        int dummy0 /* first dummy slot = 2 Tp */, const double* th2, double* my, long long& tot, long long& kept, int& zero) {
+                                        int dummy0 /* byte offset of the first dummy slot = 8 * 2 Tp */, const double* th2, double* my, long long& tot, long long& kept, int& zero) {
    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
    const int n_mine = warp < n_chunk ? (n_chunk - warp + C::CONSUMERS - 1) / C::CONSUMERS : 0;
    // prologue: fill the ring (records written with ordinary global stores in the setup pass are read by bulk copies)
@@ -580,7 +580,7 @@ em_grid_dual_kernel(DevParams p, const unsigned short* __restrict__ col16, RowRe
       // ---- setup pass
       long long tot = 0, kept = 0;
       int zero = 0;
-      g6_pass<C, true>(p, col16, rec_cta, rp + ra, kbase, r0 + ra, rb - ra, n_chunk, ring, 2 * Tp, th2, my_acc, tot, kept, zero);
+      g6_pass<C, true>(p, col16, rec_cta, rp + ra, kbase, r0 + ra, rb - ra, n_chunk, ring, 16 * Tp, th2, my_acc, tot, kept, zero);
       tot = warp_sum_ll(tot);
       kept = warp_sum_ll(kept);
       if (lane == 0 && (tot | kept)) {
@@ -620,7 +620,7 @@ em_grid_dual_kernel(DevParams p, const unsigned short* __restrict__ col16, RowRe
             iters = it + 1;
             zero = 0;
             long long d0 = 0, d1 = 0;
-            g6_pass<C, false>(p, col16, rec_cta, rp + ra, kbase, r0 + ra, rb - ra, n_chunk, ring, 2 * Tp, th2, my_acc, d0, d1, zero);
+            g6_pass<C, false>(p, col16, rec_cta, rp + ra, kbase, r0 + ra, rb - ra, n_chunk, ring, 16 * Tp, th2, my_acc, d0, d1, zero);
             zero = __syncthreads_or(zero);
             if (zero && tid == 0) atomicOr(&gs.zero_flag[item], 1);
             for (int j = tid; j < T; j += C::NT) my_partial[j] = fold(j);
