@@ -236,6 +236,17 @@ dual_prepare_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, c
 // ------------------------------------------------------------------------------------------------------------------
 // consumer side
 // ------------------------------------------------------------------------------------------------------------------
+#ifdef SBQ_G6_PHASES
+// debug build: clock cycles a warp spends per phase of its turns (printed by lane 0 of warp 0 of CTA 0 per locus)
+struct G6Phases { long long wait, decode, load, refill, ephase, mphase, other, turns; };
+__device__ G6Phases g6_ph;
+#define G6_TICK(field) { const long long now_ = clock64(); if ((threadIdx.x & 31) == 0 && threadIdx.x < 32 && blockIdx.x == 0) g6_ph.field += now_ - g6_t_; g6_t_ = now_; }
+#define G6_TICK_DECL long long g6_t_ = clock64();
+#else
+#define G6_TICK(field)
+#define G6_TICK_DECL
+#endif
+
 struct G6Ring {      // the private ring of one warp
    char* stage;      // spw stages
    uint64_t* full;   // [spw]
@@ -290,7 +301,7 @@ template <bool SETUP, int LS, typename Refill>
 __device__ __forceinline__ void g6_turn_steps(const DevParams& p, const double* __restrict__ a_s, const unsigned short* __restrict__ c_s, const unsigned (&cw0)[G6_NR],
                                               const unsigned (&cw1)[G6_NR], unsigned (&kk)[G6_NR], const int (&ne)[G6_NR], unsigned flagged, RowRec* rec_g0,
                                               const int32_t* cnt_g0, int32_t* neff_g0, int n_here, int dummy0, const double* th2, double* my, long long& tot,
-                                              long long& kept, int& zero, Refill& refill) {
+                                              long long& kept, int& zero, Refill& refill, long long& g6_t_) {
    const int lane = threadIdx.x & 31, x = lane & 15;
    const bool is_lo = lane < 16;
    double pr[G6_NR][LS];          // alpha (SETUP) or alpha * theta
@@ -313,7 +324,9 @@ __device__ __forceinline__ void g6_turn_steps(const DevParams& p, const double* 
    }
    // everything this turn needs from the stage now sits in registers: the stage can be refilled while the turn computes
    __syncwarp();
+   G6_TICK(load)
    refill();
+   G6_TICK(refill)
    const char* th2b = reinterpret_cast<const char*>(th2);
    char* myb = reinterpret_cast<char*>(my);
    // E-phase
@@ -347,33 +360,32 @@ __device__ __forceinline__ void g6_turn_steps(const DevParams& p, const double* 
             d[q] += pr[q][e];
          }
       }
+      // the four row sums of a half-warp in five shuffles (transposing butterfly): afterwards every lane holds the total of
+      // row 2 * bit3 + bit2 of its lane id; it forms that row's r = n / d (one division per lane instead of four) and the
+      // four ratios are broadcast from lanes 0, 4, 8, 12 of the half-warp
+      static_assert(G6_NR == 4, "the transposing reduction is written for four rows per half-warp");
+      const bool b3 = lane & 8, b2 = lane & 4;
+      double s0 = b3 ? d[2] : d[0], s1 = b3 ? d[3] : d[1];
+      const double o0 = b3 ? d[0] : d[2], o1 = b3 ? d[1] : d[3];
+      s0 += __shfl_xor_sync(0xffffffffu, o0, 8);
+      s1 += __shfl_xor_sync(0xffffffffu, o1, 8);
+      double u = b2 ? s1 : s0;
+      const double ox = b2 ? s0 : s1;
+      u += __shfl_xor_sync(0xffffffffu, ox, 4);
+      u += __shfl_xor_sync(0xffffffffu, u, 2);
+      u += __shfl_xor_sync(0xffffffffu, u, 1);
+      const int n_mine = b3 ? (b2 ? ne[3] : ne[2]) : (b2 ? ne[1] : ne[0]);
+      const bool live = n_mine >= 0;
+      const bool safe = u > 1e-290 && u < 1e290;   // the straight-line division's range; anything else (never seen on real data) divides in IEEE
+      if (live && u == 0) zero = 1;
+      double rm = fast_div_pos((double)max(n_mine, 0), safe ? u : 1.0);
+      if (live && u != 0 && !safe) rm = (double)n_mine / u;
+      rm = (live && u != 0) ? rm : 0.0;
+      const int hb = lane & 16;
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) {
-#pragma unroll
-         for (int q = 0; q < G6_NR; ++q) d[q] += __shfl_xor_sync(0xffffffffu, d[q], o);
-      }
-      // r_q = n_q / d_q, four independent straight-line divisions; denominators outside the fast path's range (never seen on
-      // real data) take the IEEE division afterwards
-      bool odd = false;
-      double dd[G6_NR];
-#pragma unroll
-      for (int q = 0; q < G6_NR; ++q) {
-         const bool live = ne[q] >= 0;
-         const bool safe = d[q] > 1e-290 && d[q] < 1e290;
-         if (live && d[q] == 0) zero = 1;
-         odd |= live && d[q] != 0 && !safe;
-         dd[q] = safe ? d[q] : 1.0;
-      }
-#pragma unroll
-      for (int q = 0; q < G6_NR; ++q) r[q] = fast_div_pos((double)max(ne[q], 0), dd[q]);
-#pragma unroll
-      for (int q = 0; q < G6_NR; ++q) r[q] = (ne[q] >= 0 && d[q] > 1e-290 && d[q] < 1e290) ? r[q] : 0.0;
-      if (odd) {
-#pragma unroll
-         for (int q = 0; q < G6_NR; ++q)
-            if (ne[q] >= 0 && d[q] != 0 && !(d[q] > 1e-290 && d[q] < 1e290)) r[q] = (double)ne[q] / d[q];
-      }
+      for (int q = 0; q < G6_NR; ++q) r[q] = __shfl_sync(0xffffffffu, rm, hb + 4 * q);
    }
+   G6_TICK(ephase)
    // M-phase: rows in order (two rows of a half-warp may share a column), inside a row the low half-warp first. A row's
    // slots are distinct, so its loads are issued together, then its stores.
 #pragma unroll
@@ -390,12 +402,13 @@ __device__ __forceinline__ void g6_turn_steps(const DevParams& p, const double* 
          __syncwarp();
       }
    }
+   G6_TICK(mphase)
 }
 
 template <bool SETUP, typename Refill>
 __device__ __forceinline__ unsigned g6_turn(const DevParams& p, const double* __restrict__ a_s, const unsigned short* __restrict__ c_s, const RowRec* rec0,
                                             RowRec* rec_g0, const int32_t* cnt_g0, int32_t* neff_g0, int n_here, uint32_t ck0, int dummy0,
-                                            const double* th2, double* my, long long& tot, long long& kept, int& zero, Refill refill) {
+                                            const double* th2, double* my, long long& tot, long long& kept, int& zero, Refill refill, long long& g6_t_) {
    const int x = threadIdx.x & 15;
    int ne[G6_NR];
    unsigned flagged = 0;
@@ -415,10 +428,11 @@ __device__ __forceinline__ unsigned g6_turn(const DevParams& p, const double* __
       kk[q] = nk.y - ck0 + x;
    }
    L = max(L, __shfl_xor_sync(0xffffffffu, L, 16));   // steps of the longest of the warp's eight rows
+   G6_TICK(decode)
    // straight-line bodies for 4, 5 and 6 steps (a row's fullest bank holds 4 entries in ~70 % of the rows, 5 in most others)
-   if (SETUP || L > 5) g6_turn_steps<SETUP, 6>(p, a_s, c_s, cw0, cw1, kk, ne, flagged, rec_g0, cnt_g0, neff_g0, n_here, dummy0, th2, my, tot, kept, zero, refill);
-   else if (L == 5) g6_turn_steps<SETUP, 5>(p, a_s, c_s, cw0, cw1, kk, ne, flagged, rec_g0, cnt_g0, neff_g0, n_here, dummy0, th2, my, tot, kept, zero, refill);
-   else g6_turn_steps<SETUP, 4>(p, a_s, c_s, cw0, cw1, kk, ne, flagged, rec_g0, cnt_g0, neff_g0, n_here, dummy0, th2, my, tot, kept, zero, refill);
+   if (SETUP || L > 5) g6_turn_steps<SETUP, 6>(p, a_s, c_s, cw0, cw1, kk, ne, flagged, rec_g0, cnt_g0, neff_g0, n_here, dummy0, th2, my, tot, kept, zero, refill, g6_t_);
+   else if (L == 5) g6_turn_steps<SETUP, 5>(p, a_s, c_s, cw0, cw1, kk, ne, flagged, rec_g0, cnt_g0, neff_g0, n_here, dummy0, th2, my, tot, kept, zero, refill, g6_t_);
+   else g6_turn_steps<SETUP, 4>(p, a_s, c_s, cw0, cw1, kk, ne, flagged, rec_g0, cnt_g0, neff_g0, n_here, dummy0, th2, my, tot, kept, zero, refill, g6_t_);
    return flagged;
 }
 
@@ -459,7 +473,9 @@ __device__ __forceinline__ void g6_pass(const DevParams& p, const unsigned short
       }
    }
    __syncwarp();
+   long long g6_t_ = clock64();
    for (int i = 0; i < n_mine; ++i) {
+      G6_TICK(other)
       const int c = warp + i * C::CONSUMERS;
       const int sidx = ring.next;
       // boundaries of the chunk that will refill this stage, fetched now so that the loads overlap the turn
@@ -468,6 +484,10 @@ __device__ __forceinline__ void g6_pass(const DevParams& p, const unsigned short
       if (lane == 0 && cn < n_chunk) { kn0 = rp_cta[min(cn * C::CROWS, n_rows)]; kn1 = rp_cta[min((cn + 1) * C::CROWS, n_rows)]; }
       const int i0 = c * C::CROWS, i1 = min(i0 + C::CROWS, n_rows);       // rows of the chunk (CTA-local)
       mbar_wait(&ring.full[sidx], (ring.phase >> sidx) & 1u);
+      G6_TICK(wait)
+#ifdef SBQ_G6_PHASES
+      if (threadIdx.x == 0 && blockIdx.x == 0) ++g6_ph.turns;
+#endif
       ring.phase ^= 1u << sidx;
       ring.next = sidx + 1 == ring.spw ? 0 : sidx + 1;
       char* st = ring.stage + (size_t)sidx * C::STAGE_BYTES;
@@ -484,7 +504,7 @@ __device__ __forceinline__ void g6_pass(const DevParams& p, const unsigned short
          const int64_t k0 = kbase + ck0;
          const unsigned fl = g6_turn<SETUP>(p, (const double*)st + (k0 & 1), (const unsigned short*)(st + C::C_OFF) + (k0 & 7), rec_s + (min(h0, i1 - 1) - i0),
                                             rec_cta + h0, p.count + row_abs0 + h0, p.neff + row_abs0 + h0, max(0, min(G6_NR, i1 - h0)), ck0, dummy0, th2, my,
-                                            tot, kept, zero, refill);
+                                            tot, kept, zero, refill, g6_t_);
          walk = __shfl_sync(0xffffffffu, fl, 0) | (__shfl_sync(0xffffffffu, fl, 16) << G6_NR);
       } else {
          walk = (1u << C::CROWS) - 1u;
@@ -693,6 +713,12 @@ em_grid_dual_kernel(DevParams p, const unsigned short* __restrict__ col16, RowRe
       }
       grid.sync();   // scratch (partial, theta_next) is reused by the next locus
    }
+#ifdef SBQ_G6_PHASES
+   if (b == 0 && tid == 0 && g6_ph.turns)
+      printf("G6PHASES turns %lld per-turn cycles: wait %lld decode %lld load %lld refill %lld E %lld M %lld other %lld\n", g6_ph.turns, g6_ph.wait / g6_ph.turns,
+             g6_ph.decode / g6_ph.turns, g6_ph.load / g6_ph.turns, g6_ph.refill / g6_ph.turns, g6_ph.ephase / g6_ph.turns, g6_ph.mphase / g6_ph.turns,
+             g6_ph.other / g6_ph.turns);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------------
