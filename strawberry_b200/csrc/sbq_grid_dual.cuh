@@ -88,13 +88,17 @@ constexpr int G6_PREP_WARPS = 8;
 constexpr int G6_PSTRIDE = G6_MAXROW + 1;   // odd byte stride between the rows of a tile
 
 struct G6PrepTile {
-   unsigned char bank_a[32][G6_PSTRIDE];   // bank of slot A per entry; overwritten by (destination | slot choice << 7)
-   unsigned char bank_b[32][G6_PSTRIDE];
+   unsigned char bank_a[32][G6_PSTRIDE];   // bit 0-3: bank of slot A, bit 7: the entry uses slot B; finally (destination | slot choice << 7)
+   unsigned char bank_b[32][G6_PSTRIDE];   // bank of slot B
+   unsigned char col_hi[32][G6_PSTRIDE];   // column >> 4 (column = col_hi << 4 | bank of slot A)
    unsigned char load[16][32], fill[16][32], pos[16][32];   // per-lane scratch, [bank][lane]: conflict-free
    unsigned char pre[G6_LMAX + 1][32];
    unsigned char cnt[32][8];               // record bytes of the 32 rows
+   unsigned char cand[32];                 // row takes part in the sorted layout so far
 };
 
+// Rows r and r + 4 of an 8-row group are updated TOGETHER by the two half-warps of a warp (em_grid_dual_kernel, M-phase),
+// so their slot sets must be disjoint: a column both rows hold gets slot A in one row and slot B in the other.
 __global__ void __launch_bounds__(G6_PREP_WARPS * 32)
 dual_prepare_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, const int64_t* __restrict__ rec_off, RowRec* __restrict__ recs,
                     unsigned short* __restrict__ col16) {
@@ -116,49 +120,86 @@ dual_prepare_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, c
          rec_l[R].cnt[lane] = 0;
          if (lane == 0) { rec_l[R].neff = -1; rec_l[R].koff = (uint32_t)(rp[R] - kbase); }
       }
-      for (int64_t tile0 = wid * 32; tile0 < R; tile0 += nw * 32) {
+      for (int64_t tile0 = wid * 32; tile0 < R; tile0 += nw * 32) {   // tiles start at multiples of 32 rows: whole 8-row groups
          const int nrow = (int)min((int64_t)32, R - tile0);
-         // my row (lane-per-row phase): extent and whether it takes the sorted layout at all
          const int64_t my_k0 = lane < nrow ? rp[tile0 + lane] : 0, my_k1 = lane < nrow ? rp[tile0 + lane + 1] : 0;
          const int my_n = (int)min((int64_t)(G6_MAXROW + 1), my_k1 - my_k0);
-         // phase A: stage the bank pairs of the 32 rows
+         tl.cand[lane] = lane < nrow && my_n <= G6_MAXROW;
+         __syncwarp();
+         // phase A (whole warp): stage bank pairs and column high bits of the 32 rows; a row whose columns are not strictly
+         // ascending (the pairing below merges two rows' column lists) stays in CSR order
          for (int r = 0; r < nrow; ++r) {
             const int64_t k0 = __shfl_sync(0xffffffffu, my_k0, r);
             const int n = __shfl_sync(0xffffffffu, my_n, r);
             if (n > G6_MAXROW) continue;
+            bool bad = false;
             for (int idx = lane; idx < n; idx += 32) {
                const int c = p.col[k0 + idx];
+               if (idx > 0 && p.col[k0 + idx - 1] >= c) bad = true;
                tl.bank_a[r][idx] = (unsigned char)(c & 15);
                tl.bank_b[r][idx] = (unsigned char)((c + (c >> 4)) & 15);
+               tl.col_hi[r][idx] = (unsigned char)(c >> 4);
             }
+            if (__any_sync(0xffffffffu, bad) && lane == 0) tl.cand[r] = 0;
          }
          __syncwarp();
-         // phase B: lane = row. Two-choice allocation: greedy least-loaded bank, then two sweeps that move an entry to its
-         // other bank when that lowers the larger of the two loads.
-         bool sorted = lane < nrow && my_n <= G6_MAXROW;
-         if (sorted) {
+         // phase B1 (lane = row): two-choice allocation - greedy least-loaded bank, then two sweeps that move an entry to its
+         // other bank when that lowers the larger of the two loads
+         const bool cand = tl.cand[lane];
+         if (cand) {
             const int n = my_n;
 #pragma unroll
             for (int b = 0; b < 16; ++b) tl.load[b][lane] = 0;
-            unsigned pick[3] = {0u, 0u, 0u};   // bit e: entry e uses slot B
             for (int e = 0; e < n; ++e) {
                const int ba = tl.bank_a[lane][e], bb = tl.bank_b[lane][e];
                const bool pk = tl.load[bb][lane] < tl.load[ba][lane];
-               if (pk) pick[e >> 5] |= 1u << (e & 31);
+               if (pk) tl.bank_a[lane][e] = (unsigned char)(ba | 0x80);
                ++tl.load[pk ? bb : ba][lane];
             }
             for (int sweep = 0; sweep < 2; ++sweep) {
                for (int e = 0; e < n; ++e) {
-                  const int ba = tl.bank_a[lane][e], bb = tl.bank_b[lane][e];
-                  const bool pk = (pick[e >> 5] >> (e & 31)) & 1u;
+                  const int va = tl.bank_a[lane][e], ba = va & 15, bb = tl.bank_b[lane][e];
+                  const bool pk = va & 0x80;
                   const int cur = pk ? bb : ba, alt = pk ? ba : bb;
                   if (tl.load[cur][lane] > tl.load[alt][lane] + 1) {
                      --tl.load[cur][lane];
                      ++tl.load[alt][lane];
-                     pick[e >> 5] ^= 1u << (e & 31);
+                     tl.bank_a[lane][e] = (unsigned char)(va ^ 0x80);
                   }
                }
             }
+         }
+         __syncwarp();
+         // phase B2 (one lane per pair of rows r, r + 4): a column held by both rows must use different slots
+         const int n_partner = __shfl_sync(0xffffffffu, my_n, lane ^ 4);
+         if ((lane & 4) == 0 && cand && tl.cand[lane + 4]) {
+            const int r1 = lane, r2 = lane + 4, n1 = my_n, n2 = n_partner;
+            int e1 = 0, e2 = 0;
+            while (e1 < n1 && e2 < n2) {
+               const int v1 = tl.bank_a[r1][e1], v2 = tl.bank_a[r2][e2];
+               const int c1 = (tl.col_hi[r1][e1] << 4) | (v1 & 15), c2 = (tl.col_hi[r2][e2] << 4) | (v2 & 15);
+               if (c1 < c2) { ++e1; continue; }
+               if (c2 < c1) { ++e2; continue; }
+               if ((v1 & 0x80) == (v2 & 0x80)) {
+                  // same slot in both rows: flip the entry whose other bank is the emptier one
+                  const int ba = v1 & 15, bb = tl.bank_b[r1][e1];   // same column: same bank pair in both rows
+                  const bool pk = v1 & 0x80;
+                  const int cur = pk ? bb : ba, alt = pk ? ba : bb;
+                  const int rr = tl.load[alt][r1] <= tl.load[alt][r2] ? r1 : r2;
+                  --tl.load[cur][rr];
+                  ++tl.load[alt][rr];
+                  if (rr == r1) tl.bank_a[r1][e1] = (unsigned char)(v1 ^ 0x80);
+                  else tl.bank_a[r2][e2] = (unsigned char)(v2 ^ 0x80);
+               }
+               ++e1;
+               ++e2;
+            }
+         }
+         __syncwarp();
+         // phase B3 (lane = row): step layout
+         bool sorted = cand;
+         if (sorted) {
+            const int n = my_n;
             int L = 0;
 #pragma unroll
             for (int b = 0; b < 16; ++b) L = max(L, (int)tl.load[b][lane]);
@@ -185,8 +226,9 @@ dual_prepare_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, c
                tl.cnt[lane][6] = 0;
                tl.cnt[lane][7] = (unsigned char)steps;
                for (int e = 0; e < n; ++e) {
-                  const bool pk = (pick[e >> 5] >> (e & 31)) & 1u;
-                  const int bk = pk ? tl.bank_b[lane][e] : tl.bank_a[lane][e];
+                  const int va = tl.bank_a[lane][e];
+                  const bool pk = va & 0x80;
+                  const int bk = pk ? tl.bank_b[lane][e] : (va & 15);
                   const int sq = tl.fill[bk][lane]++;
                   tl.bank_a[lane][e] = (unsigned char)((tl.pre[sq][lane] + tl.pos[bk][lane]) | (pk ? 0x80 : 0));
                }
@@ -197,7 +239,7 @@ dual_prepare_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, c
             for (int s = 0; s < 8; ++s) tl.cnt[lane][s] = s == 0 ? G6_FLAG : 0;
          }
          __syncwarp();
-         // phase C: permute the rows in place (alpha) and write slots and records
+         // phase C (whole warp): permute the rows in place (alpha) and write slots and records
          for (int r = 0; r < nrow; ++r) {
             const int64_t k0 = __shfl_sync(0xffffffffu, my_k0, r), k1 = __shfl_sync(0xffffffffu, my_k1, r);
             const bool srt = __shfl_sync(0xffffffffu, (int)sorted, r);
@@ -229,6 +271,57 @@ dual_prepare_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, c
             }
          }
          __syncwarp();
+      }
+   }
+}
+
+// Debug check of the prepared layout (SBQ_DUAL_VERIFY=1; used by the tests): one warp per 8-row group counts (a) steps whose
+// entries do not sit in 16 distinct banks, (b) slots held by both rows r and r + 4 of the group, (c) slots repeated in a row.
+__global__ void __launch_bounds__(256)
+dual_verify_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, const int64_t* __restrict__ rec_off, const RowRec* __restrict__ recs,
+                   const unsigned short* __restrict__ col16, int* __restrict__ violations) {
+   const int lane = threadIdx.x & 31;
+   const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+   for (int item = 0; item < n_list; ++item) {
+      const int l = list[item];
+      const int64_t r0 = p.loc_row_off[l];
+      const int64_t R = p.loc_row_off[l + 1] - r0;
+      const int64_t kbase = p.row_ptr[r0];
+      const RowRec* rec_l = recs + rec_off[item];
+      for (int64_t g = wid; g * 8 < R; g += nw) {
+         int bad = 0;
+         for (int q = 0; q < 8; ++q) {
+            const int64_t row = g * 8 + q;
+            if (row >= R || rec_l[row].cnt[0] == G6_FLAG) continue;
+            const int64_t k0 = kbase + rec_l[row].koff, k1 = kbase + rec_l[row + 1].koff;
+            // (a) banks inside every step
+            int64_t k = k0;
+            int total = 0;
+            for (int e = 0; e < G6_LMAX; ++e) {
+               const int ce = rec_l[row].cnt[e];
+               const int bank = lane < ce ? (col16[k + lane] >> 3) & 15 : -1 - lane;
+               for (int y = 0; y < 16; ++y) {
+                  const int by = __shfl_sync(0xffffffffu, bank, y);
+                  if (lane < ce && y != lane && by == bank) bad = 1;
+               }
+               if (ce > 16) bad = 1;
+               k += ce;
+               total += ce;
+            }
+            if (total != (int)(k1 - k0)) bad = 1;
+            // (c) slots inside the row, (b) against the partner row
+            const int64_t prow = row + 4;
+            const bool pair = (q & 4) == 0 && prow < R && rec_l[prow].cnt[0] != G6_FLAG;
+            const int64_t pk0 = pair ? kbase + rec_l[prow].koff : 0, pk1 = pair ? kbase + rec_l[prow + 1].koff : 0;
+            for (int64_t x = k0 + lane; x < k1; x += 32) {
+               const unsigned short sx = col16[x];
+               for (int64_t y = k0; y < k1; ++y)
+                  if (y != x && col16[y] == sx) bad = 1;
+               for (int64_t y = pk0; y < pk1; ++y)
+                  if (col16[y] == sx) bad = 1;
+            }
+         }
+         if (__any_sync(0xffffffffu, bad) && lane == 0) atomicAdd(violations, 1);
       }
    }
 }
@@ -386,21 +479,17 @@ __device__ __forceinline__ void g6_turn_steps(const DevParams& p, const double* 
       for (int q = 0; q < G6_NR; ++q) r[q] = __shfl_sync(0xffffffffu, rm, hb + 4 * q);
    }
    G6_TICK(ephase)
-   // M-phase: rows in order (two rows of a half-warp may share a column), inside a row the low half-warp first. A row's
-   // slots are distinct, so its loads are issued together, then its stores.
+   // M-phase: the rows of a half-warp one after the other (they may share a slot); the two half-warps update their q-th rows
+   // TOGETHER - the prepare pass made the slot sets of rows r and r + 4 of every 8-row group disjoint, and a row's own slots
+   // are distinct, so the loads of a step group are issued together, then the stores.
 #pragma unroll
    for (int q = 0; q < G6_NR; ++q) {
+      double o[LS];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-         if ((h == 0) == is_lo) {
-            double o[LS];
+      for (int e = 0; e < LS; ++e) o[e] = *reinterpret_cast<double*>(myb + so[q][e]);
 #pragma unroll
-            for (int e = 0; e < LS; ++e) o[e] = *reinterpret_cast<double*>(myb + so[q][e]);
-#pragma unroll
-            for (int e = 0; e < LS; ++e) *reinterpret_cast<double*>(myb + so[q][e]) = fma(pr[q][e], r[q], o[e]);
-         }
-         __syncwarp();
-      }
+      for (int e = 0; e < LS; ++e) *reinterpret_cast<double*>(myb + so[q][e]) = fma(pr[q][e], r[q], o[e]);
+      __syncwarp();
    }
    G6_TICK(mphase)
 }
@@ -804,6 +893,17 @@ inline int grid_dual_launch(const DevParams& dp, int64_t nnz_total, const int32_
       if (cudaFuncSetAttribute(dual_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem) != cudaSuccess) return -3;
       dual_prepare_kernel<<<prop.multiProcessorCount * 2, G6_PREP_WARPS * 32, psmem, st>>>(dp, d_list, n_list, d_rec_off, d_recs, (unsigned short*)*bf.col16);
       ++*n_launch;
+      if (getenv("SBQ_DUAL_VERIFY")) {   // tests: the prepared layout must satisfy the kernel's conflict-freedom assumptions
+         int* d_viol = nullptr;
+         int h_viol = -1;
+         if (cudaMalloc(&d_viol, sizeof(int)) != cudaSuccess) return -4;
+         cudaMemsetAsync(d_viol, 0, sizeof(int), st);
+         dual_verify_kernel<<<prop.multiProcessorCount * 4, 256, 0, st>>>(dp, d_list, n_list, d_rec_off, d_recs, (const unsigned short*)*bf.col16, d_viol);
+         cudaMemcpyAsync(&h_viol, d_viol, sizeof(int), cudaMemcpyDeviceToHost, st);
+         cudaStreamSynchronize(st);
+         cudaFree(d_viol);
+         if (h_viol != 0) { fprintf(stderr, "sbq: two-slot layout check failed: %d groups violate it\n", h_viol); return -7; }
+      }
    }
    const char* env_nc = getenv("SBQ_DUAL_NC");   // tuning: force the number of warps
    const int force_nc = env_nc ? atoi(env_nc) : 0;

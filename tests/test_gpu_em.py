@@ -267,6 +267,7 @@ def test_grid_tier_two_slot_layout_edge_shapes(q, oracle_mod, monkeypatch):
     b = synth.concat([_two_slot_edge_locus(9001, 733, 11), synth.giant(n_loci=1, rows_per_locus=4503, seed=4), _two_slot_edge_locus(3001, 90, 12)])
     ora = oracle_mod.quantify_batch(b, b["total_mapped_reads"], n_threads=2)
     monkeypatch.setenv("SBQ_GRID_DUAL", "1")   # read by the planner when the batch is submitted
+    monkeypatch.setenv("SBQ_DUAL_VERIFY", "1")   # libsbq checks the prepared layout: distinct banks per step, disjoint slots of rows r, r + 4
     res = run_gpu(q, b, 3, 0)
     assert res["stats"]["loci_grid"] == 3
     assert_matches_oracle(res, ora, b, "two-slot grid kernel")
