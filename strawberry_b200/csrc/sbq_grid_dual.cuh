@@ -38,7 +38,8 @@ constexpr int G6_MAXROW = 96;                    // longest row the sorted layou
 constexpr unsigned char G6_FLAG = 255;           // cnt[0] of a row left in CSR order
 
 struct __align__(16) RowRec {
-   unsigned char cnt[8];     // cnt[e], e < 6: entries of step e (<= 16, descending); cnt[7]: number of steps
+   unsigned char cnt[8];     // cnt[e], e < 6: entries of step e (<= 16, descending); cnt[7]: number of steps;
+                             // cnt[6]: summary of the row's 8-row group: most steps of its rows | 0x80 if a row of it is left in CSR order
    int32_t neff;             // effective count (-1: dropped by the row filter)
    uint32_t koff;            // first non-zero of the row, relative to the locus' first non-zero
 };
@@ -223,7 +224,6 @@ dual_prepare_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, c
                   if (s < G6_LMAX) { tl.cnt[lane][s] = (unsigned char)cn; steps += cn > 0; }
                   acc += cn;
                }
-               tl.cnt[lane][6] = 0;
                tl.cnt[lane][7] = (unsigned char)steps;
                for (int e = 0; e < n; ++e) {
                   const int va = tl.bank_a[lane][e];
@@ -237,6 +237,16 @@ dual_prepare_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, c
          if (lane < nrow && !sorted) {
 #pragma unroll
             for (int s = 0; s < 8; ++s) tl.cnt[lane][s] = s == 0 ? G6_FLAG : 0;
+         }
+         {  // summary of every 8-row group (8 consecutive lanes): most steps, any row left in CSR order
+            int gs = (lane < nrow && sorted) ? (int)tl.cnt[lane][7] : 0;
+            int gf = (lane < nrow && !sorted) ? 1 : 0;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+               gs = max(gs, __shfl_xor_sync(0xffffffffu, gs, o));
+               gf |= __shfl_xor_sync(0xffffffffu, gf, o);
+            }
+            if (lane < nrow) tl.cnt[lane][6] = (unsigned char)(gs | (gf ? 0x80 : 0));
          }
          __syncwarp();
          // phase C (whole warp): permute the rows in place (alpha) and write slots and records
@@ -496,27 +506,41 @@ __device__ __forceinline__ void g6_turn_steps(const DevParams& p, const double* 
 
 template <bool SETUP, typename Refill>
 __device__ __forceinline__ unsigned g6_turn(const DevParams& p, const double* __restrict__ a_s, const unsigned short* __restrict__ c_s, const RowRec* rec0,
-                                            RowRec* rec_g0, const int32_t* cnt_g0, int32_t* neff_g0, int n_here, uint32_t ck0, int dummy0,
+                                            RowRec* rec_g0, const int32_t* cnt_g0, int32_t* neff_g0, int n_here, bool complete, uint32_t ck0, int dummy0,
                                             const double* th2, double* my, long long& tot, long long& kept, int& zero, Refill refill, long long& g6_t_) {
    const int x = threadIdx.x & 15;
    int ne[G6_NR];
    unsigned flagged = 0;
    int L = 0;
    unsigned cw0[G6_NR], cw1[G6_NR], kk[G6_NR];
+   const unsigned gsum = (complete && n_here > 0) ? rec0[0].cnt[6] : 0x80u;   // the same byte for both half-warps (same 8-row group)
+   if (!(gsum & 0x80u)) {
+      // whole chunk, every row in the sorted layout: nothing to check, the step count comes with the records
 #pragma unroll
-   for (int q = 0; q < G6_NR; ++q) {
-      const bool ex = q < n_here;
-      const uint2 cw = ex ? *reinterpret_cast<const uint2*>(rec0[q].cnt) : make_uint2(0u, 0u);
-      const uint2 nk = ex ? *reinterpret_cast<const uint2*>(&rec0[q].neff) : make_uint2(0xffffffffu, ck0);
-      const bool fl = (cw.x & 0xffu) == G6_FLAG;
-      if (fl) flagged |= 1u << q;
-      ne[q] = fl ? -1 : (int)nk.x;
-      cw0[q] = fl ? 0u : cw.x;
-      cw1[q] = fl ? 0u : cw.y;
-      L = max(L, (int)(cw1[q] >> 24));
-      kk[q] = nk.y - ck0 + x;
+      for (int q = 0; q < G6_NR; ++q) {
+         const uint4 rc = *reinterpret_cast<const uint4*>(&rec0[q]);
+         cw0[q] = rc.x;
+         cw1[q] = rc.y;
+         ne[q] = (int)rc.z;
+         kk[q] = rc.w - ck0 + x;
+      }
+      L = (int)(gsum & 7u);
+   } else {
+#pragma unroll
+      for (int q = 0; q < G6_NR; ++q) {
+         const bool ex = q < n_here;
+         const uint2 cw = ex ? *reinterpret_cast<const uint2*>(rec0[q].cnt) : make_uint2(0u, 0u);
+         const uint2 nk = ex ? *reinterpret_cast<const uint2*>(&rec0[q].neff) : make_uint2(0xffffffffu, ck0);
+         const bool fl = (cw.x & 0xffu) == G6_FLAG;
+         if (fl) flagged |= 1u << q;
+         ne[q] = fl ? -1 : (int)nk.x;
+         cw0[q] = fl ? 0u : cw.x;
+         cw1[q] = fl ? 0u : cw.y;
+         L = max(L, (int)(cw1[q] >> 24));
+         kk[q] = nk.y - ck0 + x;
+      }
+      L = max(L, __shfl_xor_sync(0xffffffffu, L, 16));   // steps of the longest of the warp's eight rows
    }
-   L = max(L, __shfl_xor_sync(0xffffffffu, L, 16));   // steps of the longest of the warp's eight rows
    G6_TICK(decode)
    // straight-line bodies for 4, 5 and 6 steps (a row's fullest bank holds 4 entries in ~70 % of the rows, 5 in most others)
    if (SETUP || L > 5) g6_turn_steps<SETUP, 6>(p, a_s, c_s, cw0, cw1, kk, ne, flagged, rec_g0, cnt_g0, neff_g0, n_here, dummy0, th2, my, tot, kept, zero, refill, g6_t_);
@@ -592,7 +616,7 @@ __device__ __forceinline__ void g6_pass(const DevParams& p, const unsigned short
       if (staged) {
          const int64_t k0 = kbase + ck0;
          const unsigned fl = g6_turn<SETUP>(p, (const double*)st + (k0 & 1), (const unsigned short*)(st + C::C_OFF) + (k0 & 7), rec_s + (min(h0, i1 - 1) - i0),
-                                            rec_cta + h0, p.count + row_abs0 + h0, p.neff + row_abs0 + h0, max(0, min(G6_NR, i1 - h0)), ck0, dummy0, th2, my,
+                                            rec_cta + h0, p.count + row_abs0 + h0, p.neff + row_abs0 + h0, max(0, min(G6_NR, i1 - h0)), i1 - i0 == C::CROWS, ck0, dummy0, th2, my,
                                             tot, kept, zero, refill, g6_t_);
          walk = __shfl_sync(0xffffffffu, fl, 0) | (__shfl_sync(0xffffffffu, fl, 16) << G6_NR);
       } else {
