@@ -837,9 +837,10 @@ em_grid_dual_kernel(DevParams p, const unsigned short* __restrict__ col16, RowRe
 // ------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------
-// The kernel pays off with 12 warps per SM (it is bound by instruction latency, not by the shared-memory pipe any more);
-// with fewer the TMA ring kernel (20 warps) is faster. 12 warps fit up to T ~ 800.
-inline bool grid_dual_supports_iso(int T) { return T <= G6_MAX_ISO && G6Cfg<12>::fits(T, 1); }
+// The kernel is bound by instruction latency, so it lives on warps per SM: 0.143 / 0.160 / 0.172 / 0.217 ms per pass with
+// 12 / 10 / 8 / 6 warps on the configs[3] shape, against 0.2045 ms for the TMA ring kernel. It is used where at least 8
+// warps fit (T <= ~1300; 12 warps up to T ~ 800).
+inline bool grid_dual_supports_iso(int T) { return T <= G6_MAX_ISO && G6Cfg<8>::fits(T, 1); }
 inline bool grid_dual_possible(int T) { return T <= G6_MAX_ISO && G6Cfg<4>::fits(T, 1); }   // SBQ_GRID_DUAL=1 forces the kernel wherever it can run
 
 struct GridDualBufs {
