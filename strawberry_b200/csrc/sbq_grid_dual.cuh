@@ -26,7 +26,7 @@
 //
 // Rows with more than 96 non-zeros or whose fullest bank still holds more than 6 entries keep their CSR order (flag in
 // the record) and are walked by a whole warp from global memory, as are the rows of a chunk fuller than a stage.
-// Eligibility (host planner): T <= 4080, locus non-zeros < 2^32, on average <= 56 non-zeros per row, shared memory for
+// Eligibility (host planner): T <= 4048, locus non-zeros < 2^32, on average <= 56 non-zeros per row, shared memory for
 // at least 3 consumer warps. Anything else runs on em_grid_tma_kernel / em_grid_kernel.
 #pragma once
 #include "sbq_grid_tma.cuh"
@@ -48,7 +48,7 @@ static_assert(sizeof(RowRec) == 16, "one 16-byte unit per row");
 constexpr int G6_NR = 4;                         // rows a half-warp keeps in flight
 constexpr int G6_MAX_SPW = 4;                    // ring stages per warp (at most)
 constexpr int G6_MAX_WARPS = 16;
-constexpr int G6_MAX_ISO = 4080;                 // slot * 8 must fit the u16 stream: (2 Tp + 16) * 8 <= 65535
+constexpr int G6_MAX_ISO = 4048;                 // slot * 8 must fit the u16 stream: (2 Tp + 64) * 8 <= 65535
 
 __host__ __device__ __forceinline__ int g6_tp(int T) { return (T + 15) & ~15; }
 __host__ __device__ __forceinline__ int g6_slot_b(int j, int Tp) { return Tp + (j & ~15) + ((j + (j >> 4)) & 15); }
@@ -71,7 +71,7 @@ struct G6Cfg {
    static constexpr int R_OFF = C_OFF + C_BYTES;
    static constexpr int R_BYTES = (CROWS + 1) * (int)sizeof(RowRec);   // + the record after the chunk (its offset ends the chunk)
    static constexpr int STAGE_BYTES = ((R_OFF + R_BYTES + 127) / 128) * 128;
-   static size_t fixed_bytes(int T) { return (size_t)(2 * g6_tp(T) + 16) * (1 + NC) * sizeof(double); }   // th2[2Tp+16] | acc[NC][2Tp+16]
+   static size_t fixed_bytes(int T) { return (size_t)(2 * g6_tp(T) + 64) * (1 + NC) * sizeof(double); }   // th2[2Tp+64] | acc[NC][2Tp+64]
    static int stages_per_warp(int T) {   // ring depth per warp that fits beside the accumulators
       const long long room = 225LL * 1024 - (long long)fixed_bytes(T);
       long long spw = room / ((long long)STAGE_BYTES * NC);
@@ -410,6 +410,9 @@ __device__ __forceinline__ void g6_turn_steps(const DevParams& p, const double* 
    double pr[G6_NR][LS];          // alpha (SETUP) or alpha * theta
    unsigned so[G6_NR][LS];        // slot * 8 (as stored in the u16 stream): byte offset into theta (th2) and into the accumulator row (my)
    // (step-major loops: consecutive instructions belong to different rows, i.e. to independent dependency chains)
+   // Dummy slots: 64 behind the two slot ranges - per half-warp 16 by bank (lanes that hold a step-0 entry: distinct banks,
+   // so distinct slots) and 16 by lane (lanes without any entry): no two lanes of a warp ever share a dummy slot.
+   const int dbase = dummy0 + (lane & 16) * 16;
    int dummy[G6_NR];
 #pragma unroll
    for (int e = 0; e < LS; ++e) {
@@ -419,7 +422,7 @@ __device__ __forceinline__ void g6_turn_steps(const DevParams& p, const double* 
          const bool valid = (unsigned)x < ce;
          const double a = a_s[kk[q]];
          const int c = (int)c_s[kk[q]];
-         if (e == 0) dummy[q] = dummy0 + (valid ? (c & 0x78) : 8 * x);   // a lane without any entry in the row: a bank of its own choice (rare extra wavefront)
+         if (e == 0) dummy[q] = dbase + (valid ? (c & 0x78) : 128 + 8 * x);   // a lane without any entry in the row: a slot of its own (rare extra wavefront)
          pr[q][e] = (SETUP && !valid) ? 0.0 : a;   // EM: a lane without an entry reads a finite stale alpha and multiplies it by theta[dummy] = 0
          so[q][e] = (unsigned)(valid ? c : dummy[q]);
          kk[q] += ce;
@@ -668,7 +671,7 @@ em_grid_dual_kernel(DevParams p, const unsigned short* __restrict__ col16, RowRe
       const int R = (int)(p.loc_row_off[l + 1] - r0);
       const int64_t t0 = p.loc_iso_off[l];
       const int T = (int)(p.loc_iso_off[l + 1] - t0);
-      const int Tp = g6_tp(T), T2 = 2 * Tp + 16;   // two slots per column + 16 dummy slots (one per bank)
+      const int Tp = g6_tp(T), T2 = 2 * Tp + 64;   // two slots per column + 64 dummy slots
       double* th2 = (double*)(g6_smem + (size_t)ns * C::STAGE_BYTES);   // [2 Tp]: slot A | slot B
       double* acc = th2 + T2;                                           // [NC][2 Tp]
       const int64_t* __restrict__ rp = p.row_ptr + r0;
@@ -690,7 +693,7 @@ em_grid_dual_kernel(DevParams p, const unsigned short* __restrict__ col16, RowRe
          s_rows[tid] = lo;
       }
       for (int x = tid; x < C::CONSUMERS * T2; x += C::NT) acc[x] = 0.0;
-      if (tid < 16) th2[2 * Tp + tid] = 0.0;   // dummy slots read as theta = 0
+      if (tid < 64) th2[2 * Tp + tid] = 0.0;   // dummy slots read as theta = 0
       __syncthreads();
       const int ra = s_rows[0], rb = s_rows[1];
       const int n_chunk = (rb - ra + C::CROWS - 1) / C::CROWS;

@@ -33,12 +33,12 @@ def two_choice_loads(cols):
 
 
 def test_slot_maps_are_disjoint_bijections():
-    for T in (1, 15, 16, 17, 90, 718, 783, 800, 4080):
+    for T in (1, 15, 16, 17, 90, 718, 783, 800, 4048):
         Tp = tp(T)
         j = np.arange(T)
         b = slot_b(j, Tp)
         assert len(np.unique(b)) == T and b.min() >= Tp and b.max() < 2 * Tp       # slot A = j < Tp <= slot B < 2 Tp
-        assert (2 * Tp + 16) * 8 <= 65535                                          # slot * 8 fits the u16 stream
+        assert (2 * Tp + 64) * 8 <= 65535                                          # slot * 8 fits the u16 stream
         other_bank = (b & 15) != (j & 15)
         assert np.array_equal(other_bank, ((j >> 4) & 15) != 0)                    # same bank only in every 16th 16-block
 
