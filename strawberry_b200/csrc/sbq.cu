@@ -158,7 +158,9 @@ struct sbq_ctx {
    // device
    DevBuf d_in, d_out, d_lists, d_grid_scratch, d_col16, d_rowrec;
    bool col16_ready = false, grid_tma_ok = false, grid_dual_ok = false;
-   std::vector<int64_t> grid_rec_off;            // row-record offset of every grid-tier locus (+ total), list order
+   std::vector<int64_t> grid_rec_off;            // row-record offset of every two-slot-kernel locus (+ total), list order
+   size_t grid_n_dual = 0;                       // the first grid_n_dual entries of grid_list run on the two-slot kernel, the rest on the TMA ring / register-staged kernel
+   int grid_max_iso_dual = 1;
    int grid_max_iso = 1;
    int grid_variant = 0;                         // which giant-locus kernel the last solve used (sbq_launch_stat.variant)
    DevParams dp{};
@@ -295,8 +297,10 @@ int plan(sbq_ctx* c) {
    c->warp_max_iso = 1;
    c->max_iso_all = 1;
    c->grid_max_iso = 1;
+   c->grid_max_iso_dual = 1;
    c->grid_tma_ok = true;
-   c->grid_dual_ok = !getenv("SBQ_GRID_NO_DUAL");   // two-slot layout kernel (sbq_grid_dual.cuh) unless a locus does not qualify
+   c->grid_dual_ok = !getenv("SBQ_GRID_NO_DUAL");   // two-slot layout kernel (sbq_grid_dual.cuh) for the loci that qualify
+   std::vector<char> dual_locus(c->n_loci, 0);
    std::vector<int64_t> nnz_of(c->n_loci);
    LaunchClass* slot[5][4] = {};
    std::vector<LaunchClass> tmp;
@@ -320,10 +324,16 @@ int plan(sbq_ctx* c) {
          c->warp_max_iso = std::max(c->warp_max_iso, (int)T);
       } else if (tier == 3) {
          c->grid_list.push_back((int32_t)l);
-         c->grid_max_iso = std::max(c->grid_max_iso, (int)T);
-         if (!grid_tma_supports((int)T, (long long)R, c->prop.multiProcessorCount)) c->grid_tma_ok = false;
-         // bank-aligned two-slot layout: 16-bit slots, 32-bit offsets inside the locus, rows short enough on average
-         if ((!grid_dual_supports_iso((int)T) && !getenv("SBQ_GRID_DUAL")) || !grid_dual_possible((int)T) || nnz >= (1LL << 32) || nnz > 56 * R) c->grid_dual_ok = false;
+         // bank-aligned two-slot layout: 16-bit slot offsets, 32-bit offsets inside the locus, rows short enough on average
+         const bool dual = c->grid_dual_ok && (grid_dual_supports_iso((int)T) || (getenv("SBQ_GRID_DUAL") && grid_dual_possible((int)T))) &&
+                           nnz < (1LL << 32) && nnz <= 56 * R;
+         dual_locus[l] = dual;
+         if (dual) {
+            c->grid_max_iso_dual = std::max(c->grid_max_iso_dual, (int)T);
+         } else {
+            c->grid_max_iso = std::max(c->grid_max_iso, (int)T);
+            if (!grid_tma_supports((int)T, (long long)R, c->prop.multiProcessorCount)) c->grid_tma_ok = false;
+         }
       } else {
          int cs = c->force_cluster ? c->force_cluster : cluster_size_for(nnz);
          int csi = cs == 1 ? 0 : cs == 2 ? 1 : cs == 4 ? 2 : cs == 8 ? 3 : 4;
@@ -342,9 +352,12 @@ int plan(sbq_ctx* c) {
    }
    auto by_size = [&](int32_t a, int32_t b) { return nnz_of[a] != nnz_of[b] ? nnz_of[a] > nnz_of[b] : a < b; };
    std::sort(c->warp_list.begin(), c->warp_list.end(), by_size);
-   std::sort(c->grid_list.begin(), c->grid_list.end(), by_size);
-   c->grid_rec_off.assign(c->grid_list.size() + 1, 0);
-   for (size_t i = 0; i < c->grid_list.size(); ++i) {
+   // two-slot-kernel loci first, each part by descending size
+   std::sort(c->grid_list.begin(), c->grid_list.end(), [&](int32_t a, int32_t b) { return dual_locus[a] != dual_locus[b] ? dual_locus[a] > dual_locus[b] : by_size(a, b); });
+   c->grid_n_dual = 0;
+   for (int32_t l : c->grid_list) c->grid_n_dual += dual_locus[l];
+   c->grid_rec_off.assign(c->grid_n_dual + 1, 0);
+   for (size_t i = 0; i < c->grid_n_dual; ++i) {
       const int64_t R = lro[c->grid_list[i] + 1] - lro[c->grid_list[i]];
       c->grid_rec_off[i + 1] = c->grid_rec_off[i] + R + 1;
    }
@@ -802,23 +815,30 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
    if (!c->grid_list.empty()) {
       CU(cudaEventRecord(c->ev[6], st));
       int n_launch = 0;
-      int rc;
-      if (c->grid_dual_ok) {
+      int rc = 0;
+      c->grid_variant = 0;
+      const int32_t* d_grid = c->d_lists_p + c->grid_list_off;
+      const int n_dual = (int)c->grid_n_dual, n_rest = (int)c->grid_list.size() - n_dual;
+      if (n_dual) {
          GridDualBufs bf{&c->d_grid_scratch.p, &c->d_grid_scratch.cap, &c->d_col16.p, &c->d_col16.cap, &c->d_rowrec.p, &c->d_rowrec.cap};
-         rc = grid_dual_launch(c->dp, c->nnz, c->d_lists_p + c->grid_list_off, (int)c->grid_list.size(), c->grid_max_iso, c->grid_rec_off.data(),
-                              c->prop, bf, c->col16_ready, st, &n_launch);
-         if (rc == 0) c->col16_ready = true;
+         int nl = 0;
+         rc = grid_dual_launch(c->dp, c->nnz, d_grid, n_dual, c->grid_max_iso_dual, c->grid_rec_off.data(), c->prop, bf, c->col16_ready, st, &nl);
+         n_launch += nl;
          c->grid_variant = 3;
-      } else if (c->grid_tma_ok && !getenv("SBQ_GRID_NO_TMA")) {
-         c->grid_variant = 2;
-         rc = grid_tma_launch(c->dp, c->nnz, c->d_lists_p + c->grid_list_off, (int)c->grid_list.size(), c->grid_max_iso, c->prop,
-                              &c->d_grid_scratch.p, &c->d_grid_scratch.cap, &c->d_col16.p, &c->d_col16.cap, c->col16_ready, st, &n_launch);
-         if (rc == 0) c->col16_ready = true;
-      } else {
-         c->grid_variant = 1;
-         rc = grid_tier_launch(c->dp, c->d_lists_p + c->grid_list_off, (int)c->grid_list.size(), c->prop, &c->d_grid_scratch.p,
-                               &c->d_grid_scratch.cap, st, &n_launch);
       }
+      if (rc == 0 && n_rest) {   // loci the two-slot layout does not take (wide, or rows too long on average)
+         int nl = 0;
+         if (c->grid_tma_ok && !getenv("SBQ_GRID_NO_TMA")) {
+            if (!c->grid_variant) c->grid_variant = 2;
+            rc = grid_tma_launch(c->dp, c->nnz, d_grid + n_dual, n_rest, c->grid_max_iso, c->prop, &c->d_grid_scratch.p, &c->d_grid_scratch.cap,
+                                 &c->d_col16.p, &c->d_col16.cap, c->col16_ready, st, &nl);
+         } else {
+            if (!c->grid_variant) c->grid_variant = 1;
+            rc = grid_tier_launch(c->dp, d_grid + n_dual, n_rest, c->prop, &c->d_grid_scratch.p, &c->d_grid_scratch.cap, st, &nl);
+         }
+         n_launch += nl;
+      }
+      if (rc == 0) c->col16_ready = true;
       if (rc != 0) return fail(c, rc, "grid tier launch failed: %s", cudaGetErrorString(cudaGetLastError()));
       launches += n_launch;
       CU(cudaEventRecord(c->ev[7], st));

@@ -236,6 +236,20 @@ def test_grid_tier_dense_rows_take_the_oversize_chunk_path(q, oracle_mod):
     qq.close()
 
 
+def test_golden_vectors_through_the_two_slot_grid_kernel(q, monkeypatch):
+    """The reference's golden vectors (all four locus outcomes) through the grid tier: 135 of the 136 loci qualify for the
+    two-slot kernel, the one whose rows average more than 56 non-zeros runs on the TMA ring kernel in the same solve."""
+    b, theta_ref, rc_ref, iters, status = load_golden()
+    monkeypatch.setenv("SBQ_GRID_DUAL", "1")
+    monkeypatch.setenv("SBQ_DUAL_VERIFY", "1")
+    res = run_gpu(q, b, 3, 0)
+    assert res["stats"]["loci_grid"] == len(status)
+    assert any(r["kernel"] == "em_grid_dual_kernel" for r in q.launch_stats())
+    assert np.array_equal(res["status"], status) and np.array_equal(res["iters"], iters)
+    ok, worst = theta_close(res["theta"], theta_ref, b)
+    assert ok.all(), worst
+
+
 def _two_slot_edge_locus(R, T, seed):
     """A giant-tier locus for the two-slot layout (sbq_grid_dual.cuh): Poisson(40) rows plus empty rows, rows dropped by
     the row filter, rows too long for the sorted layout (walked from global memory), a run of 90-entry rows and a run of
