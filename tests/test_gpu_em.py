@@ -278,7 +278,7 @@ def test_grid_tier_two_slot_layout_edge_shapes(q, oracle_mod, monkeypatch):
     """Grid tier through the bank-aligned two-slot kernel: ragged row counts (not a multiple of the 8-row chunk), empty /
     dropped / over-long rows, over-full chunks, a 90-isoform locus (fewer than 16 banks per row in use), and a plain
     giant-shaped locus; bit-reproducible when the resident batch is solved again."""
-    b = synth.concat([_two_slot_edge_locus(9001, 733, 11), synth.giant(n_loci=1, rows_per_locus=4503, seed=4), _two_slot_edge_locus(3001, 90, 12)])
+    b = synth.concat([_two_slot_edge_locus(40001, 733, 11), synth.giant(n_loci=1, rows_per_locus=4503, seed=4), _two_slot_edge_locus(3001, 90, 12)])   # 40001 rows: > 12 chunks per CTA, the stage refill path runs
     ora = oracle_mod.quantify_batch(b, b["total_mapped_reads"], n_threads=2)
     monkeypatch.setenv("SBQ_GRID_DUAL", "1")   # read by the planner when the batch is submitted
     monkeypatch.setenv("SBQ_DUAL_VERIFY", "1")   # libsbq checks the prepared layout: distinct banks per step, disjoint slots of rows r, r + 4

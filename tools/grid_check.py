@@ -37,7 +37,7 @@ def edge_locus(R, T, seed):
                 count=count, iso_len=rng.integers(400, 8001, T).astype(np.int32), total_mapped_reads=int(count.sum()), meta={})
 
 
-rows = int(sys.argv[1]) if len(sys.argv) > 1 else 9001
+rows = int(sys.argv[1]) if len(sys.argv) > 1 else 60001   # > 12 chunks per CTA: the stage refill path runs
 max_iter = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 b = synth.concat([edge_locus(rows, 733, 11), synth.giant(n_loci=1, rows_per_locus=rows // 2 + 3, seed=4), edge_locus(rows // 3 + 1, 90, 12)])
 q = api.Quantifier(max_iter=max_iter)
