@@ -9,25 +9,31 @@
 //    slot B(j) = Tp + 16*(j/16) + ((j + j/16) mod 16) (the column's 16-block rotated by the block index: a different
 //    bank). Every non-zero may use either slot of its column, which turns "48 balls into 16 bins" into a two-choice
 //    allocation: the fullest bank drops from ~7 to ~3.85 entries.
-//  * dual_prepare_kernel (once per upload; a warp stages 32 rows, every lane allocates one row, the warp permutes) picks the slot of every non-zero (greedy least-loaded
-//    bank + two improvement sweeps) and re-sorts the row IN PLACE inside its CSR range into a jagged-diagonal order:
-//    step-major, within a step one entry per bank, banks ranked by load. Lane x of a half-warp then only ever touches
-//    bank rank x: the alpha / column reads are contiguous and the theta gather and the accumulator update are
-//    conflict-free. The u16 column copy holds the slot as a byte offset (slot * 8); a 16-byte record per row holds the per-step entry counts, the
-//    effective count and the row's offset (it replaces row pointer + count in the stream: same bytes).
-//  * em_grid_dual_kernel: persistent cooperative kernel, one CTA per SM = NC consumer warps + 1 producer warp. The
-//    producer streams 8-row chunks (alpha slab, u16 slab, record slab - three 1-D TMA bulk copies) into an NS-deep
-//    shared-memory ring; consumer warp w takes every NC-th chunk (teams of more warps per chunk are a template
-//    parameter), all 8 rows of it (four per half-warp, all in flight together: the loads of the four rows overlap, registers hold the products between
-//    the normaliser and the update). The two half-warps take turns on the warp-private accumulators (their rows may
-//    share a column), four rows one after the other.
+//  * dual_prepare_kernel (once per upload; a warp stages 32 rows, every lane allocates one row, the warp permutes) picks the
+//    slot of every non-zero (greedy least-loaded bank + two improvement sweeps) and re-sorts the row IN PLACE inside its
+//    CSR range into a jagged-diagonal order: step-major, within a step one entry per bank, banks ranked by load. Lane x
+//    of a half-warp then only ever touches bank rank x: the alpha / column reads are contiguous and the theta gather and
+//    the accumulator update are conflict-free. Rows r and r + 4 of every 8-row group - the rows the two half-warps of a
+//    warp work on at the same time - get DISJOINT slot sets (a column both hold takes slot A in one and slot B in the
+//    other), so both half-warps update the accumulators in the same instructions. The u16 column copy holds the slot as a
+//    byte offset (slot * 8); a 16-byte record per row holds the per-step entry counts, the effective count, the row's
+//    offset and a summary byte of its 8-row group (it replaces row pointer + count in the stream: same bytes).
+//  * em_grid_dual_kernel: persistent cooperative kernel, one CTA of NC warps per SM, no producer warp: warp w takes the
+//    8-row chunks w, w + NC, ... of the CTA's rows and owns a private shared-memory stage that it refills itself
+//    (alpha slab, u16 slab, record slab - three 1-D TMA bulk copies issued by lane 0, one mbarrier per stage) AS SOON AS
+//    the chunk sits in registers, so the copy overlaps the E- and M-phase of the same chunk. Eight rows per warp are in
+//    flight (four per half-warp): loads (step-major: independent rows adjacent in the instruction stream), theta gather
+//    and products, a transposing four-row shuffle reduction, one normaliser division per lane, then the accumulator
+//    update - four dependent load-add-store blocks per turn. A lane without an entry in a step works on a dummy slot of
+//    its own (theta = 0), so the steps are branch-free; straight-line bodies exist for 4, 5 and 6 steps.
 //  * reductions (warp-private accumulators -> per-CTA partial -> column owners -> theta') are those of the other grid
 //    kernels: fixed order, no floating-point atomics. Both slots of a column are summed there.
 //
-// Rows with more than 96 non-zeros or whose fullest bank still holds more than 6 entries keep their CSR order (flag in
-// the record) and are walked by a whole warp from global memory, as are the rows of a chunk fuller than a stage.
-// Eligibility (host planner): T <= 4048, locus non-zeros < 2^32, on average <= 56 non-zeros per row, shared memory for
-// at least 3 consumer warps. Anything else runs on em_grid_tma_kernel / em_grid_kernel.
+// Rows with more than 96 non-zeros, with columns that are not strictly ascending, or whose fullest bank still holds more
+// than 6 entries keep their CSR order (flag in the record) and are walked by a whole warp from global memory, as are the
+// rows of a chunk fuller than a stage. Eligibility (host planner, per locus): T <= 4048 and shared memory for at least
+// 8 warps (T <~ 1300), locus non-zeros < 2^32, on average <= 56 non-zeros per row. Anything else runs on
+// em_grid_tma_kernel / em_grid_kernel.
 #pragma once
 #include "sbq_grid_tma.cuh"
 
