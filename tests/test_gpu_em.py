@@ -292,6 +292,30 @@ def test_grid_tier_two_slot_layout_edge_shapes(q, oracle_mod, monkeypatch):
     assert np.array_equal(res["theta"], again["theta"]) and np.array_equal(res["iters"], again["iters"])
 
 
+def test_grid_tier_two_slot_rows_with_unsorted_columns(q, oracle_mod, monkeypatch):
+    """The two-slot layout pairs rows by merging their (ascending) column lists; a row whose columns are not strictly
+    ascending (out of contract: sbq_validate rejects it, but validation is optional) must stay in CSR order and be walked
+    from global memory - same results."""
+    b = _two_slot_edge_locus(3001, 300, 21)
+    rng = np.random.default_rng(5)
+    rp = b["row_ptr"]
+    for i in range(0, 3001, 3):                      # every third row: columns (and their alphas) in random order
+        k0, k1 = int(rp[i]), int(rp[i + 1])
+        perm = rng.permutation(k1 - k0)
+        b["col"][k0:k1] = b["col"][k0:k1][perm]
+        b["alpha"][k0:k1] = b["alpha"][k0:k1][perm]
+    ora = oracle_mod.quantify_batch(b, b["total_mapped_reads"])
+    monkeypatch.setenv("SBQ_GRID_DUAL", "1")
+    monkeypatch.setenv("SBQ_DUAL_VERIFY", "1")
+    q.clear()                                        # (sbq_validate rejects such input; callers may skip validation)
+    q.set_plan(3, 0)
+    q.submit_flat(b)
+    q.run(b["total_mapped_reads"])
+    res = q.results()
+    assert any(r["kernel"] == "em_grid_dual_kernel" for r in q.launch_stats())
+    assert_matches_oracle(res, ora, b, "two-slot kernel, unsorted columns")
+
+
 def _shape_locus(rng, T, R, k_mean, empty_rows=0, dropped_rows=0):
     """One locus with Poisson(k_mean) columns per row (clamped to 1..T), plus rows without entries and rows whose
     alphas are all below the row filter."""
