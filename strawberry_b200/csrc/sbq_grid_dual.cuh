@@ -412,7 +412,6 @@ __device__ __forceinline__ void g6_turn_steps(const DevParams& p, const double* 
                                               const int32_t* cnt_g0, int32_t* neff_g0, int n_here, int dummy0, const double* th2, double* my, long long& tot,
                                               long long& kept, int& zero, Refill& refill, long long& g6_t_) {
    const int lane = threadIdx.x & 31, x = lane & 15;
-   const bool is_lo = lane < 16;
    double pr[G6_NR][LS];          // alpha (SETUP) or alpha * theta
    unsigned so[G6_NR][LS];        // slot * 8 (as stored in the u16 stream): byte offset into theta (th2) and into the accumulator row (my)
    // (step-major loops: consecutive instructions belong to different rows, i.e. to independent dependency chains)
