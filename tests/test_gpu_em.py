@@ -316,6 +316,17 @@ def test_grid_tier_two_slot_rows_with_unsorted_columns(q, oracle_mod, monkeypatc
     assert_matches_oracle(res, ora, b, "two-slot kernel, unsorted columns")
 
 
+def test_grid_tier_random_sweep_against_the_oracle():
+    """tools/grid_sweep.py: eight randomised giant-tier shapes (17 to 1290 isoforms, 3 to 55 non-zeros per row, 3 to 12 345 rows,
+    zero counts, dropped rows) through the grid tier with the prepared layout verified, each against the oracle."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "grid_sweep.py")], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "grid_sweep ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def _shape_locus(rng, T, R, k_mean, empty_rows=0, dropped_rows=0):
     """One locus with Poisson(k_mean) columns per row (clamped to 1..T), plus rows without entries and rows whose
     alphas are all below the row filter."""
