@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define SBQ_ABI_VERSION 1
+#define SBQ_ABI_VERSION 2
 
 typedef enum {
    SBQ_SUCCESS = 0,
@@ -43,7 +43,10 @@ typedef enum {
  *               no isoforms at all (src/alignments.cpp:1526-1529); keep[] is 0 for all of them    */
 typedef enum { SBQ_LOCUS_OK = 0, SBQ_LOCUS_ITER_CAP = 1, SBQ_LOCUS_ZERO_DENOM = 2, SBQ_LOCUS_NO_ROWS = 3 } sbq_locus_status;
 
-#define SBQ_MAX_ISO 20000   /* isoforms per locus the kernels accept (shared-memory accumulators)   */
+/* Isoforms per locus every multi-row tier accepts: theta, the column sums and at least one private accumulator row live
+ * in shared memory (cluster tier 7 T + 64 doubles, grid tier 7 T + 16 doubles of <= 200 KB). Wider loci are refused at
+ * submit time with SBQ_ERR_UNSUPPORTED; a locus within the limit never fails an upload - it falls to the other tier. */
+#define SBQ_MAX_ISO 3600
 
 /* Replaces the reference's mutable globals read on the hot path (SURVEY section 5 "Config"). */
 typedef struct {
@@ -62,6 +65,13 @@ typedef struct {
    int32_t max_theta_it;       /* EmSolver::_max_theta_it_num        include/estimate.hpp:238  5000 */
    int32_t max_bias_it;        /* EmSolver::_max_bias_it_num         include/estimate.hpp:237    10 */
    double  bias_tol;           /* EmSolver::_bias_change_limit       include/estimate.hpp:241  1e-2 */
+   /* Multi-GPU. 0 or 1: one device (`device`). N > 1: the context drives the N devices
+    * device .. device + N - 1 (device = -1 counts from 0) from this one process: sbq_upload partitions the queued
+    * loci over them by non-zeros (greedy LPT, sbq_partition_lpt), every device solves its share with the same
+    * kernels, and the TPM denominator - the path's only exchange, src/alignments.cpp:1821-1824 - is ONE
+    * ncclAllReduce(ncclDouble, count 1) over the devices (NCCL is loaded on first use; single-device contexts
+    * never touch it). Results come back in submit order, independent of the partition. */
+   int32_t n_gpus;
 } sbq_config;
 
 /* One locus as the host class-table builder emits it: what LocusContext::estimate_abundances
@@ -176,6 +186,15 @@ typedef struct {
    int64_t max_iters;       /* longest EM run among its loci (the launch's critical path)                 */
 } sbq_launch_stat;
 int  sbq_get_launch_stats(const sbq_ctx*, sbq_launch_stat* out, int cap);
+
+/* Greedy longest-processing-time partition of n loci with the given costs over n_parts devices: loci by descending
+ * cost (ties: lower index first) onto the currently lightest part (ties: lower part first). owner[l] receives the part
+ * of locus l. Host-only and deterministic - it is what sbq_upload runs for n_gpus > 1 with cost = nnz + rows + isoforms
+ * (loci are never split across devices). */
+int  sbq_partition_lpt(const int64_t* cost, int64_t n, int32_t n_parts, int32_t* owner);
+
+/* Multi-GPU contexts: device ordinal that solved each queued locus (valid after sbq_upload); single-device: all equal. */
+int  sbq_locus_devices(sbq_ctx*, int32_t* device_of_locus);
 
 /* Single-locus convenience backing a drop-in EmSolver (EmSolver::init + run, src/estimate.cpp:366-488):
  * theta receives n_iso doubles; returns the sbq_locus_status (>= 0) or a negative sbq_error. */

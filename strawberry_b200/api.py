@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "sbq_submit", "sbq_submit_flat", "sbq_clear", "sbq_validate", "sbq_host_alloc", "sbq_host_free",
     "sbq_upload", "sbq_solve", "sbq_download", "sbq_run", "sbq_fpkm_sum", "sbq_fpkm_sum_to_device",
     "sbq_finalize_tpm", "sbq_results", "sbq_get_stats", "sbq_get_launch_stats", "sbq_em_solve", "sbq_set_plan",
-    "sbq_set_covariates", "sbq_bias_results",
+    "sbq_set_covariates", "sbq_bias_results", "sbq_partition_lpt", "sbq_locus_devices",
 ]
 
 
@@ -41,7 +41,7 @@ class Config(ctypes.Structure):
                 ("row_eps", ctypes.c_double), ("min_iso_frac", ctypes.c_double),
                 ("effective_len_norm", ctypes.c_int32), ("insert_mean", ctypes.c_double),
                 ("bias_mode", ctypes.c_int32), ("max_out_it", ctypes.c_int32), ("max_theta_it", ctypes.c_int32),
-                ("max_bias_it", ctypes.c_int32), ("bias_tol", ctypes.c_double)]
+                ("max_bias_it", ctypes.c_int32), ("bias_tol", ctypes.c_double), ("n_gpus", ctypes.c_int32)]
 
 
 class Locus(ctypes.Structure):
@@ -103,6 +103,8 @@ def lib():
         L.sbq_set_plan.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         L.sbq_set_covariates.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32]
         L.sbq_bias_results.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.sbq_partition_lpt.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p]
+        L.sbq_locus_devices.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         _lib = L
     return _lib
 
@@ -148,6 +150,16 @@ def pinned_batch(batch):
         a[...] = batch[k]
         out[k] = a
     return out
+
+
+def partition_lpt(cost, n_parts):
+    """sbq_partition_lpt: owner[l] of the greedy LPT partition the multi-GPU context uses (host-only, no device needed)."""
+    cost = _c(cost, np.int64)
+    owner = np.empty(len(cost), np.int32)
+    rc = lib().sbq_partition_lpt(_ptr(cost), len(cost), int(n_parts), _ptr(owner))
+    if rc:
+        raise SbqError(rc, lib().sbq_error_string(rc).decode())
+    return owner
 
 
 class Quantifier:
@@ -263,13 +275,20 @@ class Quantifier:
         return s.as_dict()
 
     def launch_stats(self):
-        buf = (LaunchStat * 32)()
-        n = self._chk(self._L.sbq_get_launch_stats(self._h, buf, 32))
+        cap = 32 * max(1, int(self.cfg.n_gpus))
+        buf = (LaunchStat * cap)()
+        n = self._chk(self._L.sbq_get_launch_stats(self._h, buf, cap))
         names = {1: "em_warp_kernel", 2: "em_cluster_kernel", 3: "em_grid_kernel"}
         grid = {1: "em_grid_kernel", 2: "em_grid_tma_kernel", 3: "em_grid_dual_kernel"}
         return [dict(kernel=grid.get(buf[i].variant, names[buf[i].kind]) if buf[i].kind == 3 else names[buf[i].kind], cluster_size=buf[i].cluster_size, lanes_per_row=buf[i].lanes_per_row,
                      n_loci=buf[i].n_loci, nnz=buf[i].nnz, ms=buf[i].ms, alg_bytes=buf[i].alg_bytes,
-                     frag_iters=buf[i].frag_iters, max_iters=buf[i].max_iters) for i in range(min(n, 32))]
+                     frag_iters=buf[i].frag_iters, max_iters=buf[i].max_iters) for i in range(min(n, cap))]
+
+    def locus_devices(self):
+        """device ordinal that solved each queued locus (multi-GPU contexts partition loci by non-zeros)"""
+        out = np.empty(self.stats()["n_loci"], np.int32)
+        self._chk(self._L.sbq_locus_devices(self._h, _ptr(out)))
+        return out
 
     def results(self):
         st = self.stats()

@@ -11,9 +11,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <nccl.h>   // types and prototypes only: the library itself is dlopen'ed by multi-GPU contexts (NcclApi below)
 
 #include "../../include/sbq.h"
 #include "../../include/sbq_builder.h"
@@ -97,8 +101,11 @@ struct LaunchTimer {      // CUDA events around one kernel launch, on the stream
 
 }  // namespace
 
+struct MultiState;   // n_gpus > 1: one child context per device + the NCCL communicators (defined further down)
+
 struct sbq_ctx {
    sbq_config cfg;
+   MultiState* multi = nullptr;
    int device = 0;
    cudaDeviceProp prop;
    cudaStream_t stream = nullptr;
@@ -121,8 +128,10 @@ struct sbq_ctx {
    const int32_t *b_col = nullptr, *b_count = nullptr, *b_iso_len = nullptr;
    const double* b_alpha = nullptr;
    int64_t n_loci = 0, n_row = 0, n_iso = 0, nnz = 0;
-   bool in_deferred_submit = false;
-   std::mutex deferred_mu;   // serialises sbq_submit_deferred calls (descriptor order must match CSR order)
+   bool host_released = false;   // a borrowed batch was uploaded: the caller may have freed its arrays, nothing on the host side may be re-read
+   // per-locus shape and fragment total, captured by plan() while the host arrays are still valid (metric accounting)
+   struct LocusMeta { int64_t nnz, frags; int32_t R, T; };
+   std::vector<LocusMeta> meta;
 
    // bias mode
    PinnedVec<double> h_cov;
@@ -156,7 +165,7 @@ struct sbq_ctx {
    size_t warp_list_off = 0, grid_list_off = 0;
 
    // device
-   DevBuf d_in, d_out, d_lists, d_grid_scratch, d_col16, d_rowrec;
+   DevBuf d_in, d_out, d_lists, d_grid_scratch, d_col16, d_rowrec, d_csc;
    bool col16_ready = false, grid_tma_ok = false, grid_dual_ok = false;
    std::vector<int64_t> grid_rec_off;            // row-record offset of every two-slot-kernel locus (+ total), list order
    size_t grid_n_dual = 0;                       // the first grid_n_dual entries of grid_list run on the two-slot kernel, the rest on the TMA ring / register-staged kernel
@@ -219,6 +228,7 @@ bool is_pinned(const void* p) {
 // copy a borrowed batch into our own staging (needed before anything else is appended)
 int materialise(sbq_ctx* c) {
    if (!c->borrowed) return SBQ_SUCCESS;
+   if (c->host_released) return fail(c, SBQ_ERR_STATE, "the borrowed batch was released by sbq_upload: sbq_clear and submit again");
    bool ok = true;
    c->h_loc_row_off.clear(); c->h_loc_iso_off.clear(); c->h_row_ptr.clear();
    c->h_col.clear(); c->h_count.clear(); c->h_iso_len.clear(); c->h_alpha.clear();
@@ -235,6 +245,8 @@ int materialise(sbq_ctx* c) {
 
 void reset_batch(sbq_ctx* c) {
    c->borrowed = false;
+   c->host_released = false;
+   c->meta.clear();
    c->h_loc_row_off.clear(); c->h_loc_iso_off.clear(); c->h_row_ptr.clear();
    c->h_col.clear(); c->h_count.clear(); c->h_iso_len.clear(); c->h_alpha.clear();
    c->n_loci = c->n_row = c->n_iso = c->nnz = 0;
@@ -300,16 +312,22 @@ int plan(sbq_ctx* c) {
    c->grid_max_iso_dual = 1;
    c->grid_tma_ok = true;
    c->grid_dual_ok = !getenv("SBQ_GRID_NO_DUAL");   // two-slot layout kernel (sbq_grid_dual.cuh) for the loci that qualify
+   const bool force_dual = getenv("SBQ_GRID_DUAL") != nullptr;
    std::vector<char> dual_locus(c->n_loci, 0);
    std::vector<int64_t> nnz_of(c->n_loci);
    LaunchClass* slot[5][4] = {};
    std::vector<LaunchClass> tmp;
    tmp.reserve(20);
    const int64_t grid_min_nnz = 300 * 1000;   // above this a locus is faster on the whole GPU than on a 16-CTA cluster
+   const int32_t* cnt = countp(c);
+   c->meta.resize((size_t)c->n_loci);
    for (int64_t l = 0; l < c->n_loci; ++l) {
       const int64_t R = lro[l + 1] - lro[l], T = lio[l + 1] - lio[l];
       const int64_t nnz = rp[lro[l + 1]] - rp[lro[l]];
       nnz_of[l] = nnz;
+      int64_t frags = 0;
+      for (int64_t i = lro[l]; i < lro[l + 1]; ++i) frags += cnt[i];
+      c->meta[l] = {nnz, frags, (int32_t)R, (int32_t)T};
       c->max_iso_all = std::max(c->max_iso_all, (int)T);
       if (T > SBQ_MAX_ISO) return fail(c, SBQ_ERR_UNSUPPORTED, "locus %lld has %lld isoforms (> SBQ_MAX_ISO)", (long long)l, (long long)T);
       int tier;
@@ -318,14 +336,20 @@ int plan(sbq_ctx* c) {
       else if (nnz >= grid_min_nnz) tier = 3;
       else tier = 2;
       if (tier == 1 && T > WT_MAX_ISO) tier = 2;
+      // every T <= SBQ_MAX_ISO fits both the cluster tier (streaming accumulators) and the register-staged grid kernel;
+      // the checks stay so that a future change of either limit degrades to the other tier instead of failing the upload
       if (tier == 3 && !grid_tier_supports((int)T)) tier = 2;
+      if (tier == 2 && cluster_stream_groups((int)T, SMEM_CAP, CL_NT) <= 0) {
+         if (!grid_tier_supports((int)T)) return fail(c, SBQ_ERR_UNSUPPORTED, "locus %lld: %lld isoforms fit no tier", (long long)l, (long long)T);
+         tier = 3;
+      }
       if (tier == 1) {
          c->warp_list.push_back((int32_t)l);
          c->warp_max_iso = std::max(c->warp_max_iso, (int)T);
       } else if (tier == 3) {
          c->grid_list.push_back((int32_t)l);
          // bank-aligned two-slot layout: 16-bit slot offsets, 32-bit offsets inside the locus, rows short enough on average
-         const bool dual = c->grid_dual_ok && (grid_dual_supports_iso((int)T) || (getenv("SBQ_GRID_DUAL") && grid_dual_possible((int)T))) &&
+         const bool dual = c->grid_dual_ok && (grid_dual_supports_iso((int)T) || (force_dual && grid_dual_possible((int)T))) &&
                            nnz < (1LL << 32) && nnz <= 56 * R;
          dual_locus[l] = dual;
          if (dual) {
@@ -417,7 +441,66 @@ int launch_cluster_class_nt(sbq_ctx* c, const LaunchClass& lc, cudaStream_t st) 
    return SBQ_SUCCESS;
 }
 
+// Snapshot of the staging sizes, restored when a submit fails half-way (a failed call leaves the queue unchanged).
+struct StagingMark {
+   size_t lro, lio, rp, col, al, cnt, il, wseg, wn, wmask, wlen, wpool;
+   int64_t n_loci, n_row, n_iso, nnz;
+   explicit StagingMark(const sbq_ctx* c)
+       : lro(c->h_loc_row_off.n), lio(c->h_loc_iso_off.n), rp(c->h_row_ptr.n), col(c->h_col.n), al(c->h_alpha.n), cnt(c->h_count.n), il(c->h_iso_len.n),
+         wseg(c->h_wseg.n), wn(c->h_wn.n), wmask(c->h_wmask.n), wlen(c->h_wlen.n), wpool(c->h_wpool.n),
+         n_loci(c->n_loci), n_row(c->n_row), n_iso(c->n_iso), nnz(c->nnz) {}
+   void restore(sbq_ctx* c) const {
+      c->h_loc_row_off.n = lro; c->h_loc_iso_off.n = lio; c->h_row_ptr.n = rp; c->h_col.n = col; c->h_alpha.n = al; c->h_count.n = cnt; c->h_iso_len.n = il;
+      c->h_wseg.n = wseg; c->h_wn.n = wn; c->h_wmask.n = wmask; c->h_wlen.n = wlen; c->h_wpool.n = wpool;
+      c->n_loci = n_loci; c->n_row = n_row; c->n_iso = n_iso; c->nnz = nnz;
+   }
+};
+
+// Append loci to the staged batch; the caller holds c->mu. Every locus is validated (shape, pointers, monotone row_ptr)
+// BEFORE anything is appended, and a failed allocation rolls the staging back: an error return leaves the queue as it was.
+int submit_locked(sbq_ctx* c, const sbq_locus* loci, int64_t n_loci) {
+   if (c->host_released) return fail(c, SBQ_ERR_STATE, "the borrowed batch was released by sbq_upload: sbq_clear and submit again");
+   for (int64_t l = 0; l < n_loci; ++l) {
+      const sbq_locus& L = loci[l];
+      if (L.n_iso < 1 || L.n_row < 0 || !L.row_ptr || !L.iso_len || (L.n_row > 0 && !L.count))
+         return fail(c, SBQ_ERR_INVALID, "locus %lld: bad shape or null pointer", (long long)l);
+      if (L.n_iso > SBQ_MAX_ISO) return fail(c, SBQ_ERR_UNSUPPORTED, "locus %lld: %d isoforms > SBQ_MAX_ISO", (long long)l, L.n_iso);
+      for (int32_t i = 1; i <= L.n_row; ++i)
+         if (L.row_ptr[i] < L.row_ptr[i - 1]) return fail(c, SBQ_ERR_INVALID, "locus %lld: row_ptr not monotone", (long long)l);
+      if (L.row_ptr[L.n_row] > L.row_ptr[0] && (!L.col || !L.alpha)) return fail(c, SBQ_ERR_INVALID, "locus %lld: null col / alpha", (long long)l);
+   }
+   cudaSetDevice(c->device);
+   int rc = materialise(c);
+   if (rc) return rc;
+   if ((rc = ensure_origin(c))) return rc;
+   const StagingMark mark(c);
+   for (int64_t l = 0; l < n_loci; ++l) {
+      const sbq_locus& L = loci[l];
+      const int64_t k0 = L.row_ptr[0], k1 = L.row_ptr[L.n_row];
+      const int64_t base = c->nnz - k0;
+      bool ok = c->h_row_ptr.reserve(c->h_row_ptr.n + L.n_row);
+      if (ok) {
+         for (int32_t i = 1; i <= L.n_row; ++i) c->h_row_ptr.p[c->h_row_ptr.n++] = L.row_ptr[i] + base;
+         ok = c->h_col.append(L.col + k0, k1 - k0) && c->h_alpha.append(L.alpha + k0, k1 - k0) &&
+              c->h_count.append(L.count, L.n_row) && c->h_iso_len.append(L.iso_len, L.n_iso);
+      }
+      c->nnz += k1 - k0;
+      c->n_row += L.n_row;
+      c->n_iso += L.n_iso;
+      c->n_loci += 1;
+      ok = ok && c->h_loc_row_off.append(&c->n_row, 1) && c->h_loc_iso_off.append(&c->n_iso, 1);
+      if (!ok) {
+         mark.restore(c);
+         return fail(c, SBQ_ERR_NOMEM, "pinned staging");
+      }
+   }
+   c->resident = c->solved = c->downloaded = false;
+   return SBQ_SUCCESS;
+}
+
 }  // namespace
+
+#include "sbq_multi.cuh"
 
 // ================================================================================================
 extern "C" {
@@ -454,6 +537,7 @@ void sbq_config_default(sbq_config* cfg) {
    cfg->max_theta_it = 5000;
    cfg->max_bias_it = 10;
    cfg->bias_tol = 1e-2;
+   cfg->n_gpus = 1;
 }
 
 int sbq_create(const sbq_config* cfg, sbq_ctx** out) {
@@ -461,6 +545,7 @@ int sbq_create(const sbq_config* cfg, sbq_ctx** out) {
    *out = nullptr;
    if (cfg->max_iter < 1 || !(cfg->theta_tol >= 0) || cfg->bias_mode < 0 || cfg->bias_mode > 1) return SBQ_ERR_INVALID;
    if (cfg->bias_mode == 1 && (cfg->max_out_it < 1 || cfg->max_theta_it < 1 || cfg->max_bias_it < 1 || !(cfg->bias_tol >= 0))) return SBQ_ERR_INVALID;
+   if (cfg->n_gpus < 0 || cfg->n_gpus > 64) return SBQ_ERR_INVALID;
    int ndev = 0;
    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
       cudaGetLastError();
@@ -468,9 +553,11 @@ int sbq_create(const sbq_config* cfg, sbq_ctx** out) {
    }
    int dev = cfg->device;
    if (dev < 0) {
-      if (cudaGetDevice(&dev) != cudaSuccess) return SBQ_ERR_NO_DEVICE;
+      if (cfg->n_gpus > 1) dev = 0;   // a multi-GPU context counts its devices from 0 unless told otherwise
+      else if (cudaGetDevice(&dev) != cudaSuccess) return SBQ_ERR_NO_DEVICE;
    }
    if (dev >= ndev) return SBQ_ERR_INVALID;
+   if (cfg->n_gpus > 1 && dev + cfg->n_gpus > ndev) return SBQ_ERR_NO_DEVICE;
    sbq_ctx* c = new sbq_ctx();
    c->cfg = *cfg;
    c->device = dev;
@@ -488,12 +575,20 @@ int sbq_create(const sbq_config* cfg, sbq_ctx** out) {
       if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(SBQ_ERR_CUDA);
    for (auto& t : c->lt)
       if (cudaEventCreate(&t.e0) != cudaSuccess || cudaEventCreate(&t.e1) != cudaSuccess) return bail(SBQ_ERR_CUDA);
+   if (cfg->n_gpus > 1) {
+      const int rc = multi_create(c, ndev);
+      if (rc) {
+         fprintf(stderr, "libsbq: %s\n", c->err.c_str());
+         return bail(rc);
+      }
+   }
    *out = c;
    return SBQ_SUCCESS;
 }
 
 void sbq_destroy(sbq_ctx* c) {
    if (!c) return;
+   multi_destroy(c);
    cudaSetDevice(c->device);
    if (c->stream) cudaStreamSynchronize(c->stream);
    c->h_loc_row_off.release(); c->h_loc_iso_off.release(); c->h_row_ptr.release();
@@ -501,7 +596,7 @@ void sbq_destroy(sbq_ctx* c) {
    c->h_lists.release();
    c->r_theta.release(); c->r_fpkm.release(); c->r_frac.release(); c->r_tpm.release();
    c->r_locus_fpkm.release(); c->r_keep.release(); c->r_iters.release(); c->r_status.release();
-   c->d_in.release(); c->d_out.release(); c->d_lists.release(); c->d_grid_scratch.release(); c->d_col16.release(); c->d_rowrec.release(); c->d_bias.release();
+   c->d_in.release(); c->d_out.release(); c->d_lists.release(); c->d_grid_scratch.release(); c->d_col16.release(); c->d_rowrec.release(); c->d_csc.release(); c->d_bias.release();
    c->h_cov.release(); c->r_beta.release(); c->r_outer.release();
    c->h_wseg.release(); c->h_wn.release(); c->h_wmask.release(); c->h_wpool.release(); c->h_wlen.release(); c->d_weights.release();
    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -534,36 +629,10 @@ int sbq_clear(sbq_ctx* c) {
 int sbq_submit(sbq_ctx* c, const sbq_locus* loci, int64_t n_loci) {
    if (!c || (!loci && n_loci > 0) || n_loci < 0) return SBQ_ERR_INVALID;
    std::lock_guard<std::mutex> lk(c->mu);
-   cudaSetDevice(c->device);
-   if (c->deferred == 1 && !c->in_deferred_submit) return fail(c, SBQ_ERR_STATE, "a batch is either all deferred-weight or all host-weighted");
-   if (!c->in_deferred_submit && n_loci > 0) c->deferred = 2;
-   int rc = materialise(c);
-   if (rc) return rc;
-   if ((rc = ensure_origin(c))) return rc;
-   for (int64_t l = 0; l < n_loci; ++l) {
-      const sbq_locus& L = loci[l];
-      if (L.n_iso < 1 || L.n_row < 0 || !L.row_ptr || !L.iso_len || (L.n_row > 0 && !L.count))
-         return fail(c, SBQ_ERR_INVALID, "locus %lld: bad shape or null pointer", (long long)l);
-      if (L.n_iso > SBQ_MAX_ISO) return fail(c, SBQ_ERR_UNSUPPORTED, "locus %lld: %d isoforms > SBQ_MAX_ISO", (long long)l, L.n_iso);
-      const int64_t k0 = L.row_ptr[0], k1 = L.row_ptr[L.n_row];
-      if (k1 < k0 || (k1 > k0 && (!L.col || !L.alpha))) return fail(c, SBQ_ERR_INVALID, "locus %lld: bad row_ptr", (long long)l);
-      const int64_t base = c->nnz - k0;
-      if (!c->h_row_ptr.reserve(c->h_row_ptr.n + L.n_row)) return fail(c, SBQ_ERR_NOMEM, "pinned staging");
-      for (int32_t i = 1; i <= L.n_row; ++i) {
-         if (L.row_ptr[i] < L.row_ptr[i - 1]) return fail(c, SBQ_ERR_INVALID, "locus %lld: row_ptr not monotone", (long long)l);
-         c->h_row_ptr.p[c->h_row_ptr.n++] = L.row_ptr[i] + base;
-      }
-      bool ok = c->h_col.append(L.col + k0, k1 - k0) && c->h_alpha.append(L.alpha + k0, k1 - k0) &&
-                c->h_count.append(L.count, L.n_row) && c->h_iso_len.append(L.iso_len, L.n_iso);
-      c->nnz += k1 - k0;
-      c->n_row += L.n_row;
-      c->n_iso += L.n_iso;
-      c->n_loci += 1;
-      ok = ok && c->h_loc_row_off.append(&c->n_row, 1) && c->h_loc_iso_off.append(&c->n_iso, 1);
-      if (!ok) return fail(c, SBQ_ERR_NOMEM, "pinned staging");
-   }
-   c->resident = c->solved = c->downloaded = false;
-   return SBQ_SUCCESS;
+   if (c->deferred == 1) return fail(c, SBQ_ERR_STATE, "a batch is either all deferred-weight or all host-weighted");
+   const int rc = submit_locked(c, loci, n_loci);
+   if (rc == SBQ_SUCCESS && n_loci > 0) c->deferred = 2;
+   return rc;
 }
 
 int sbq_submit_flat(sbq_ctx* c, int64_t n_loci, const int64_t* lro, const int64_t* lio, const int64_t* rp,
@@ -574,7 +643,6 @@ int sbq_submit_flat(sbq_ctx* c, int64_t n_loci, const int64_t* lro, const int64_
    std::lock_guard<std::mutex> lk(c->mu);
    cudaSetDevice(c->device);
    if (c->deferred == 1) return fail(c, SBQ_ERR_STATE, "a batch is either all deferred-weight or all host-weighted");
-   c->deferred = 2;
    const int64_t rows = lro[n_loci] - lro[0], isos = lio[n_loci] - lio[0];
    if (rows < 0 || isos < n_loci) return fail(c, SBQ_ERR_INVALID, "bad locus offsets");
    const int64_t k0 = rp[lro[0]], k1 = rp[lro[n_loci]];
@@ -591,14 +659,20 @@ int sbq_submit_flat(sbq_ctx* c, int64_t n_loci, const int64_t* lro, const int64_
       c->b_loc_row_off = lro; c->b_loc_iso_off = lio; c->b_row_ptr = rp;
       c->b_col = col; c->b_alpha = alpha; c->b_count = count; c->b_iso_len = iso_len;
       c->n_loci = n_loci; c->n_row = rows; c->n_iso = isos; c->nnz = k1;
+      c->deferred = 2;
       c->resident = c->solved = c->downloaded = false;
       return SBQ_SUCCESS;
    }
+   if (c->host_released) return fail(c, SBQ_ERR_STATE, "the borrowed batch was released by sbq_upload: sbq_clear and submit again");
+   for (int64_t i = lro[0]; i < lro[n_loci]; ++i)
+      if (rp[i + 1] < rp[i]) return fail(c, SBQ_ERR_INVALID, "row %lld: row_ptr not monotone", (long long)i);
    int rc = materialise(c);
    if (rc) return rc;
    if ((rc = ensure_origin(c))) return rc;
-   bool ok = c->h_loc_row_off.reserve(c->h_loc_row_off.n + n_loci) && c->h_loc_iso_off.reserve(c->h_loc_iso_off.n + n_loci) &&
-             c->h_row_ptr.reserve(c->h_row_ptr.n + rows);
+   // reserve everything first: nothing is appended unless all of it fits (a failed call leaves the queue unchanged)
+   const bool ok = c->h_loc_row_off.reserve(c->h_loc_row_off.n + n_loci) && c->h_loc_iso_off.reserve(c->h_loc_iso_off.n + n_loci) &&
+                   c->h_row_ptr.reserve(c->h_row_ptr.n + rows) && c->h_col.reserve(c->h_col.n + (k1 - k0)) && c->h_alpha.reserve(c->h_alpha.n + (k1 - k0)) &&
+                   c->h_count.reserve(c->h_count.n + rows) && c->h_iso_len.reserve(c->h_iso_len.n + isos);
    if (!ok) return fail(c, SBQ_ERR_NOMEM, "pinned staging");
    for (int64_t l = 1; l <= n_loci; ++l) {
       c->h_loc_row_off.p[c->h_loc_row_off.n++] = c->n_row + (lro[l] - lro[0]);
@@ -606,10 +680,12 @@ int sbq_submit_flat(sbq_ctx* c, int64_t n_loci, const int64_t* lro, const int64_
    }
    const int64_t base = c->nnz - k0;
    for (int64_t i = 1; i <= rows; ++i) c->h_row_ptr.p[c->h_row_ptr.n++] = rp[lro[0] + i] + base;
-   ok = c->h_col.append(col + k0, k1 - k0) && c->h_alpha.append(alpha + k0, k1 - k0) &&
-        c->h_count.append(count + lro[0], rows) && c->h_iso_len.append(iso_len + lio[0], isos);
-   if (!ok) return fail(c, SBQ_ERR_NOMEM, "pinned staging");
+   c->h_col.append(col + k0, k1 - k0);
+   c->h_alpha.append(alpha + k0, k1 - k0);
+   c->h_count.append(count + lro[0], rows);
+   c->h_iso_len.append(iso_len + lio[0], isos);
    c->n_loci += n_loci; c->n_row += rows; c->n_iso += isos; c->nnz += k1 - k0;
+   c->deferred = 2;
    c->resident = c->solved = c->downloaded = false;
    return SBQ_SUCCESS;
 }
@@ -617,6 +693,7 @@ int sbq_submit_flat(sbq_ctx* c, int64_t n_loci, const int64_t* lro, const int64_
 int sbq_validate(sbq_ctx* c) {
    if (!c) return SBQ_ERR_INVALID;
    std::lock_guard<std::mutex> lk(c->mu);
+   if (c->host_released) return fail(c, SBQ_ERR_STATE, "the borrowed batch was released by sbq_upload");
    const int64_t *lro = loc_row_off(c), *lio = loc_iso_off(c), *rp = row_ptr(c);
    const int32_t* col = colp(c);
    for (int64_t l = 0; l < c->n_loci; ++l) {
@@ -634,15 +711,16 @@ int sbq_validate(sbq_ctx* c) {
 
 int sbq_upload(sbq_ctx* c) {
    if (!c) return SBQ_ERR_INVALID;
+   if (c->multi) return multi_upload(c);
    std::lock_guard<std::mutex> lk(c->mu);
    CU(cudaSetDevice(c->device));
    if (c->n_loci == 0) return fail(c, SBQ_ERR_STATE, "nothing submitted");
+   if (c->host_released) return fail(c, SBQ_ERR_STATE, "the borrowed batch was released by the previous sbq_upload: sbq_clear and submit again");
    // +64 B of slack per array: the giant-locus kernel's 16-byte-granular bulk copies may read a few elements past the end
    const size_t sz_lro = align_up((c->n_loci + 1) * sizeof(int64_t)), sz_rp = align_up((c->n_row + 1) * sizeof(int64_t) + 64);
    const size_t sz_col = align_up(c->nnz * sizeof(int32_t) + 64), sz_al = align_up(c->nnz * sizeof(double) + 64);
    const size_t sz_cnt = align_up(c->n_row * sizeof(int32_t) + 64), sz_il = align_up(c->n_iso * sizeof(int32_t));
-   const size_t sz_csc = align_up(c->nnz * 4 + 16);
-   const size_t in_bytes = 2 * sz_lro + sz_rp + sz_col + sz_al + 2 * sz_cnt + sz_il + sz_csc;
+   const size_t in_bytes = 2 * sz_lro + sz_rp + sz_col + sz_al + 2 * sz_cnt + sz_il;
    const size_t sz_iso_d = align_up(c->n_iso * sizeof(double)), sz_iso_i = align_up(c->n_iso * sizeof(int32_t));
    const size_t sz_loc_i = align_up(c->n_loci * sizeof(int32_t)), sz_loc_d = align_up(c->n_loci * sizeof(double));
    const size_t out_bytes = 4 * sz_iso_d + sz_iso_i + 2 * sz_loc_i + sz_loc_d + 256;
@@ -660,7 +738,7 @@ int sbq_upload(sbq_ctx* c) {
    int32_t* d_cnt = (int32_t*)carve(sz_cnt);
    dp.neff = (int32_t*)carve(sz_cnt);
    int32_t* d_il = (int32_t*)carve(sz_il);
-   dp.csc = (unsigned*)carve(sz_csc);
+   dp.csc = nullptr;   // allocated after the plan, only when the cluster tier has loci
    dp.loc_row_off = d_lro; dp.loc_iso_off = d_lio; dp.row_ptr = d_rp; dp.col = d_col; dp.alpha = d_al;
    dp.count = d_cnt; dp.iso_len = d_il;
    p = (char*)c->d_out.p;
@@ -696,7 +774,13 @@ int sbq_upload(sbq_ctx* c) {
    }
    if (c->h_lists.n) CU(cudaMemcpyAsync(c->d_lists_p, c->h_lists.p, c->h_lists.n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
    CU(cudaEventRecord(c->ev[1], st));
+   if (!c->classes.empty()) {
+      // L2-resident overflow of the cluster tier's transposed index (4 B per non-zero, indexed like col/alpha)
+      if (!c->d_csc.reserve(align_up(c->nnz * 4 + 16))) return fail(c, SBQ_ERR_NOMEM, "device allocation failed (transposed-index scratch)");
+      dp.csc = (unsigned*)c->d_csc.p;
+   }
    CU(cudaStreamSynchronize(st));   // borrowed host arrays may be released after this returns
+   if (c->borrowed) c->host_released = true;   // from here on nothing reads the caller's arrays (metric accounting uses c->meta)
    float ms = 0;
    CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
    c->stats.upload_ms = ms;
@@ -761,6 +845,7 @@ int sbq_upload(sbq_ctx* c) {
 
 int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
    if (!c) return SBQ_ERR_INVALID;
+   if (c->multi) return multi_solve(c, total_mapped_reads);
    std::lock_guard<std::mutex> lk(c->mu);
    CU(cudaSetDevice(c->device));
    if (!c->resident) return fail(c, SBQ_ERR_STATE, "sbq_solve before sbq_upload");
@@ -839,7 +924,13 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
          n_launch += nl;
       }
       if (rc == 0) c->col16_ready = true;
-      if (rc != 0) return fail(c, rc, "grid tier launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      if (rc != 0) {
+         // the one-off layout passes permute alpha inside each giant row IN PLACE: after a failure the resident copy can no
+         // longer be trusted to match the column arrays, so the batch has to be uploaded again
+         c->resident = false;
+         c->col16_ready = false;
+         return fail(c, rc < -6 ? SBQ_ERR_CUDA : rc, "grid tier launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      }
       launches += n_launch;
       CU(cudaEventRecord(c->ev[7], st));
    }
@@ -916,6 +1007,13 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
 
 int sbq_fpkm_sum(sbq_ctx* c, double* local_sum) {
    if (!c || !local_sum) return SBQ_ERR_INVALID;
+   if (c->multi) {   // the sum over ALL devices of the context (all-reduced on the devices)
+      std::lock_guard<std::mutex> lk(c->mu);
+      if (!c->solved) return fail(c, SBQ_ERR_STATE, "sbq_fpkm_sum before sbq_solve");
+      const int rc = multi_allreduce_locked(c);
+      if (!rc) *local_sum = c->multi->global_sum;
+      return rc;
+   }
    std::lock_guard<std::mutex> lk(c->mu);
    CU(cudaSetDevice(c->device));
    if (!c->solved) return fail(c, SBQ_ERR_STATE, "sbq_fpkm_sum before sbq_solve");
@@ -926,6 +1024,14 @@ int sbq_fpkm_sum(sbq_ctx* c, double* local_sum) {
 
 int sbq_fpkm_sum_to_device(sbq_ctx* c, void* dev_double) {
    if (!c || !dev_double) return SBQ_ERR_INVALID;
+   if (c->multi) {
+      std::lock_guard<std::mutex> lk(c->mu);
+      if (!c->solved) return fail(c, SBQ_ERR_STATE, "sbq_fpkm_sum_to_device before sbq_solve");
+      const int rc = multi_allreduce_locked(c);
+      if (rc) return rc;
+      CU(cudaMemcpy(dev_double, c->multi->d_sum[0] + 1, sizeof(double), cudaMemcpyDefault));
+      return SBQ_SUCCESS;
+   }
    std::lock_guard<std::mutex> lk(c->mu);
    CU(cudaSetDevice(c->device));
    if (!c->solved) return fail(c, SBQ_ERR_STATE, "sbq_fpkm_sum_to_device before sbq_solve");
@@ -936,6 +1042,7 @@ int sbq_fpkm_sum_to_device(sbq_ctx* c, void* dev_double) {
 
 int sbq_finalize_tpm(sbq_ctx* c, double global_fpkm_sum) {
    if (!c) return SBQ_ERR_INVALID;
+   if (c->multi) return multi_finalize_tpm(c, global_fpkm_sum);
    std::lock_guard<std::mutex> lk(c->mu);
    CU(cudaSetDevice(c->device));
    if (!c->solved) return fail(c, SBQ_ERR_STATE, "sbq_finalize_tpm before sbq_solve");
@@ -949,6 +1056,7 @@ int sbq_finalize_tpm(sbq_ctx* c, double global_fpkm_sum) {
 
 int sbq_download(sbq_ctx* c) {
    if (!c) return SBQ_ERR_INVALID;
+   if (c->multi) return multi_download(c);
    std::lock_guard<std::mutex> lk(c->mu);
    CU(cudaSetDevice(c->device));
    if (!c->solved) return fail(c, SBQ_ERR_STATE, "sbq_download before sbq_solve");
@@ -982,6 +1090,10 @@ int sbq_run(sbq_ctx* c, int64_t total_mapped_reads) {
    int rc = sbq_upload(c);
    if (rc) return rc;
    if ((rc = sbq_solve(c, total_mapped_reads))) return rc;
+   if (c->multi) {   // N devices: one ncclAllReduce of the FPKM sums, TPM from the device copy of the result
+      if ((rc = multi_tpm(c))) return rc;
+      return sbq_download(c);
+   }
    double s = 0.0;
    if ((rc = sbq_fpkm_sum(c, &s))) return rc;
    if ((rc = sbq_finalize_tpm(c, s))) return rc;
@@ -995,28 +1107,23 @@ int sbq_run(sbq_ctx* c, int64_t total_mapped_reads) {
 static void account(sbq_ctx* c) {
    if (!c->stats_stale || !c->downloaded) return;
    const size_t nl = (size_t)c->n_loci;
-   const int64_t *lro = loc_row_off(c), *lio = loc_iso_off(c), *rp = row_ptr(c);
-   const int32_t* cnt = countp(c);
    std::vector<char> is_grid(nl, 0);
    for (int32_t l : c->grid_list) is_grid[l] = 1;
    int64_t it_total = 0, frag_iters = 0, alg = 0, galg = 0;
-   const bool have_host = c->borrowed || c->h_row_ptr.n > 0;
    for (auto& ls : c->launch_stats) ls.nnz = ls.alg_bytes = ls.frag_iters = ls.max_iters = 0;
-   for (size_t l = 0; l < nl && have_host; ++l) {
+   for (size_t l = 0; l < nl && l < c->meta.size(); ++l) {   // shapes captured at upload: the host arrays may be gone by now
       const int64_t it = c->r_iters.p[l];
-      const int64_t R = lro[l + 1] - lro[l], T = lio[l + 1] - lio[l], nz = rp[lro[l + 1]] - rp[lro[l]];
-      int64_t frags = 0;
-      for (int64_t i = lro[l]; i < lro[l + 1]; ++i) frags += cnt[i];
+      const sbq_ctx::LocusMeta& m = c->meta[l];
       it_total += it;
-      frag_iters += frags * it;
-      const int64_t b = (12 * nz + 12 * R + 16 * T) * it;
+      frag_iters += m.frags * it;
+      const int64_t b = (12 * m.nnz + 12 * (int64_t)m.R + 16 * (int64_t)m.T) * it;
       alg += b;
       if (is_grid[l]) galg += b;
       const int32_t li = l < c->locus_launch.size() ? c->locus_launch[l] : -1;
       if (li >= 0) {
-         c->launch_stats[li].nnz += nz;
+         c->launch_stats[li].nnz += m.nnz;
          c->launch_stats[li].alg_bytes += b;
-         c->launch_stats[li].frag_iters += frags * it;
+         c->launch_stats[li].frag_iters += m.frags * it;
          c->launch_stats[li].max_iters = std::max<int64_t>(c->launch_stats[li].max_iters, it);
       }
    }
@@ -1047,10 +1154,12 @@ int sbq_results(sbq_ctx* c, double* theta, double* fpkm, double* frac, double* t
 int sbq_get_stats(const sbq_ctx* cc, sbq_stats* out) {
    if (!cc || !out) return SBQ_ERR_INVALID;
    sbq_ctx* c = const_cast<sbq_ctx*>(cc);
-   {
-      std::lock_guard<std::mutex> lk(c->mu);
-      account(c);
+   std::lock_guard<std::mutex> lk(c->mu);
+   if (c->multi) {
+      multi_stats(c, out);
+      return SBQ_SUCCESS;
    }
+   account(c);
    *out = c->stats;
    return SBQ_SUCCESS;
 }
@@ -1073,37 +1182,38 @@ int sbq_set_insert_model(sbq_ctx* c, const sbq_insert_model* model, int32_t read
 
 int sbq_submit_deferred(sbq_ctx* c, const sbq_table* const* tables, int64_t n_tables) {
    if (!c || (!tables && n_tables > 0) || n_tables < 0) return SBQ_ERR_INVALID;
-   std::lock_guard<std::mutex> serial(c->deferred_mu);
    for (int64_t t = 0; t < n_tables; ++t) {
       sbq_locus L;
       sbq_weight_desc d;
       if (!tables[t] || sbq_table_locus(tables[t], &L) || sbq_table_weight_desc(tables[t], &d)) return SBQ_ERR_INVALID;
       const int64_t nnz = L.row_ptr[L.n_row] - L.row_ptr[0];
+      // descriptors and CSR of one table are appended under ONE lock, so concurrent submits cannot interleave them
+      std::lock_guard<std::mutex> lk(c->mu);
       if (d.n_entry != nnz) return fail(c, SBQ_ERR_INVALID, "table %lld was not built with defer_weights = 1", (long long)t);
-      {
-         std::lock_guard<std::mutex> lk(c->mu);
-         if (c->deferred == 2) return fail(c, SBQ_ERR_STATE, "a batch is either all deferred-weight or all host-weighted");
-         c->deferred = 1;
-         c->in_deferred_submit = true;
-         cudaSetDevice(c->device);
-         const int64_t pool_base = (int64_t)c->h_wpool.n;
-         bool ok = c->h_wseg.reserve(c->h_wseg.n + nnz) && c->h_wn.append(d.n_seg, nnz) && c->h_wmask.append(d.implicit_mask, nnz) &&
-                   c->h_wlen.append(d.iso_len, nnz) && c->h_wpool.append(d.pool, d.n_pool);
-         if (!ok) { c->in_deferred_submit = false; return fail(c, SBQ_ERR_NOMEM, "pinned staging"); }
-         for (int64_t k = 0; k < nnz; ++k) c->h_wseg.p[c->h_wseg.n++] = d.seg_ptr[k] < 0 ? -1 : d.seg_ptr[k] + pool_base;
+      if (c->deferred == 2) return fail(c, SBQ_ERR_STATE, "a batch is either all deferred-weight or all host-weighted");
+      cudaSetDevice(c->device);
+      const StagingMark mark(c);
+      const int64_t pool_base = (int64_t)c->h_wpool.n;
+      const bool ok = c->h_wseg.reserve(c->h_wseg.n + nnz) && c->h_wn.append(d.n_seg, nnz) && c->h_wmask.append(d.implicit_mask, nnz) &&
+                      c->h_wlen.append(d.iso_len, nnz) && c->h_wpool.append(d.pool, d.n_pool);
+      if (!ok) {
+         mark.restore(c);
+         return fail(c, SBQ_ERR_NOMEM, "pinned staging");
       }
-      const int rc = sbq_submit(c, &L, 1);
-      {
-         std::lock_guard<std::mutex> lk(c->mu);
-         c->in_deferred_submit = false;
+      for (int64_t k = 0; k < nnz; ++k) c->h_wseg.p[c->h_wseg.n++] = d.seg_ptr[k] < 0 ? -1 : d.seg_ptr[k] + pool_base;
+      const int rc = submit_locked(c, &L, 1);
+      if (rc) {
+         mark.restore(c);   // the descriptors go with the locus that was refused
+         return rc;
       }
-      if (rc) return rc;
+      c->deferred = 1;
    }
    return SBQ_SUCCESS;
 }
 
 int sbq_fetch_alpha(sbq_ctx* c, double* alpha) {
    if (!c || !alpha) return SBQ_ERR_INVALID;
+   if (c->multi) return fail(c, SBQ_ERR_UNSUPPORTED, "sbq_fetch_alpha is single-device");
    std::lock_guard<std::mutex> lk(c->mu);
    CU(cudaSetDevice(c->device));
    if (!c->resident) return fail(c, SBQ_ERR_STATE, "sbq_fetch_alpha before sbq_upload");
@@ -1130,6 +1240,24 @@ int sbq_bias_results(sbq_ctx* c, double* beta, int32_t* outer_iters) {
    std::lock_guard<std::mutex> lk(c->mu);
    CU(cudaSetDevice(c->device));
    if (c->cfg.bias_mode != 1 || !c->solved) return fail(c, SBQ_ERR_STATE, "sbq_bias_results needs a solved bias-mode batch");
+   if (c->multi) {   // per-device results scattered back into submit order
+      MultiState& m = *c->multi;
+      const size_t K = (size_t)c->n_cov;
+      for (size_t i = 0; i < m.child.size(); ++i) {
+         const size_t n = m.loci_of[i].size();
+         if (!n) continue;
+         std::vector<double> b(n * K + 1);
+         std::vector<int32_t> o(n);
+         const int rc = sbq_bias_results(m.child[i], b.data(), o.data());
+         if (rc) return fail(c, rc, "device %d: %s", m.devices[i], m.child[i]->err.c_str());
+         for (size_t x = 0; x < n; ++x) {
+            const int32_t l = m.loci_of[i][x];
+            if (beta && K) memcpy(beta + (size_t)l * K, b.data() + x * K, K * 8);
+            if (outer_iters) outer_iters[l] = o[x];
+         }
+      }
+      return SBQ_SUCCESS;
+   }
    const size_t K = (size_t)c->n_cov, nl = (size_t)c->n_loci;
    if (!c->r_beta.reserve(nl * K + 1) || !c->r_outer.reserve(nl)) return fail(c, SBQ_ERR_NOMEM, "pinned result buffers");
    if (K) CU(cudaMemcpyAsync(c->r_beta.p, c->bpar.beta, nl * K * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1143,13 +1271,43 @@ int sbq_bias_results(sbq_ctx* c, double* beta, int32_t* outer_iters) {
 int sbq_get_launch_stats(const sbq_ctx* cc, sbq_launch_stat* out, int cap) {
    if (!cc || (!out && cap > 0)) return SBQ_ERR_INVALID;
    sbq_ctx* c = const_cast<sbq_ctx*>(cc);
-   {
-      std::lock_guard<std::mutex> lk(c->mu);
-      account(c);
+   std::lock_guard<std::mutex> lk(c->mu);
+   if (c->multi) {   // the children's records, device after device
+      int n = 0;
+      for (sbq_ctx* ch : c->multi->child) {
+         const int k = sbq_get_launch_stats(ch, out && n < cap ? out + n : nullptr, n < cap ? cap - n : 0);
+         if (k > 0) n += k;
+      }
+      return n;
    }
+   account(c);
    const int n = (int)c->launch_stats.size();
    for (int i = 0; i < n && i < cap; ++i) out[i] = c->launch_stats[i];
    return n;
+}
+
+int sbq_partition_lpt(const int64_t* cost, int64_t n, int32_t n_parts, int32_t* owner) {
+   if (n < 0 || n_parts < 1 || (n > 0 && (!cost || !owner))) return SBQ_ERR_INVALID;
+   std::vector<int64_t> order((size_t)n);
+   for (int64_t i = 0; i < n; ++i) order[i] = i;
+   std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return cost[a] != cost[b] ? cost[a] > cost[b] : a < b; });
+   std::vector<int64_t> load((size_t)n_parts, 0);
+   for (int64_t l : order) {
+      int32_t best = 0;
+      for (int32_t q = 1; q < n_parts; ++q)
+         if (load[q] < load[best]) best = q;
+      owner[l] = best;
+      load[best] += cost[l];
+   }
+   return SBQ_SUCCESS;
+}
+
+int sbq_locus_devices(sbq_ctx* c, int32_t* device_of_locus) {
+   if (!c || !device_of_locus) return SBQ_ERR_INVALID;
+   std::lock_guard<std::mutex> lk(c->mu);
+   if (!c->resident) return fail(c, SBQ_ERR_STATE, "sbq_locus_devices before sbq_upload");
+   for (int64_t l = 0; l < c->n_loci; ++l) device_of_locus[l] = c->multi ? c->multi->devices[c->multi->owner[l]] : c->device;
+   return SBQ_SUCCESS;
 }
 
 int sbq_em_solve(sbq_ctx* c, const sbq_locus* locus, double* theta, int32_t* iters) {

@@ -1333,4 +1333,11 @@ __global__ void tpm_kernel(const double* __restrict__ fpkm, double* __restrict__
    if (i < n) tpm[i] = 1e6 * fpkm[i] / total;
 }
 
+// same, with the denominator read from device memory (multi-GPU: the all-reduced sum never visits the host)
+__global__ void tpm_dev_kernel(const double* __restrict__ fpkm, double* __restrict__ tpm, int64_t n, const double* __restrict__ total) {
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   const double tot = *total;
+   if (i < n) tpm[i] = 1e6 * fpkm[i] / tot;
+}
+
 }  // namespace sbq

@@ -37,7 +37,7 @@ def test_defaults_follow_the_reference(sbq_lib_path):
     assert cfg.theta_tol == 1e-2         # include/estimate.hpp:240
     assert cfg.row_eps == 1e-5           # src/estimate.cpp:381
     assert cfg.bias_mode == 0 and cfg.effective_len_norm == 0
-    assert api.lib().sbq_abi_version() == 1
+    assert api.lib().sbq_abi_version() == 2 and cfg.n_gpus == 1
     assert b"no CUDA device" in api.lib().sbq_error_string(api.SBQ_ERR_NO_DEVICE)
 
 

@@ -126,6 +126,21 @@ def test_em_solver_mirror_keeps_reference_semantics(q, oracle_mod):
     assert em2._theta == [3.5, 3.5]
 
 
+def test_full_size_config2_matches_oracle(q, oracle_mod):
+    """BASELINE configs[1] at FULL size - the exact batch bench.py times (seed 2, 20 000 loci, 10 M fragments,
+    4.82 M non-zeros) - against the CPU oracle: equal status and iteration count for every locus,
+    theta / FPKM / frac / TPM within 1e-6 relative, equal keep flags. The oracle needs well under a second."""
+    b = synth.human_shaped(seed=2)
+    ora = oracle_mod.quantify_batch(b, b["total_mapped_reads"], n_threads=8)
+    res = run_gpu(q, b)
+    assert res["stats"]["n_loci"] == 20000 and res["stats"]["nnz"] == int(b["row_ptr"][-1])
+    worst = assert_matches_oracle(res, ora, b, "configs[1] full size")
+    assert worst < 1e-6
+    frag = np.add.reduceat(b["count"].astype(np.int64), b["loc_row_off"][:-1])
+    assert res["stats"]["frag_iters"] == int((frag * ora["iters"]).sum())
+    assert res["stats"]["em_iters_total"] == int(ora["iters"].sum())
+
+
 def test_full_size_config2_properties(q):
     """BASELINE configs[1] at full size: 20k loci / 10M fragments. Oracle-free, size-independent checks."""
     b = synth.human_shaped()

@@ -43,3 +43,55 @@ def test_two_gpus_match_one(tmp_path):
     for k in ("theta", "fpkm", "frac", "keep", "iters", "status"):
         assert np.array_equal(got[k], one[k], equal_nan=True), k
     assert np.allclose(got["tpm"], one["tpm"], rtol=1e-12, equal_nan=True)
+
+
+def _multi_vs_single(n_gpus, batch, **cfg):
+    from strawberry_b200 import api
+    one = api.Quantifier(device=0, **cfg)
+    one.submit_flat(batch)
+    one.run(batch["total_mapped_reads"])
+    ref = one.results()
+    one.close()
+    q = api.Quantifier(device=0, n_gpus=n_gpus, **cfg)
+    q.submit_flat(batch)
+    q.run(batch["total_mapped_reads"])
+    got, st, dev = q.results(), q.stats(), q.locus_devices()
+    q.close()
+    return ref, got, st, dev
+
+
+@pytest.mark.parametrize("n_gpus", [2, 4, 8])
+def test_c_abi_multi_gpu_context_matches_one_gpu(n_gpus):
+    """sbq_config.n_gpus = N inside ONE process (no torch.distributed): LPT partition in sbq_upload, one ncclAllReduce of the
+    FPKM sums, results back in submit order. theta / FPKM / frac / keep / iters / status bitwise equal to one GPU, TPM up to
+    the order of one sum; every device gets loci."""
+    import torch
+    if torch.cuda.device_count() < n_gpus:
+        pytest.skip(f"needs {n_gpus} GPUs")
+    from strawberry_b200 import synth
+    b = synth.concat([synth.human_shaped(n_loci=3000, total_fragments=1_500_000, seed=77), synth.giant(n_loci=2, rows_per_locus=20_000, seed=4)])
+    ref, got, st, dev = _multi_vs_single(n_gpus, b, min_iso_frac=0.01)
+    for k in ("theta", "fpkm", "frac", "keep", "iters", "status"):
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
+    assert np.allclose(got["tpm"], ref["tpm"], rtol=1e-12, equal_nan=True)
+    assert sorted(set(dev.tolist())) == list(range(n_gpus))
+    assert st["n_loci"] == 3002 and st["nnz"] == int(b["row_ptr"][-1])
+
+
+def test_c_abi_multi_gpu_fewer_loci_than_devices():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from strawberry_b200 import synth
+    b = synth.human_shaped(n_loci=1, total_fragments=5_000, seed=3)
+    ref, got, st, dev = _multi_vs_single(2, b)
+    for k in ("theta", "fpkm", "frac", "tpm", "keep", "iters", "status"):
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
+
+
+def test_c_abi_n_gpus_beyond_the_box_is_refused():
+    import torch
+    from strawberry_b200 import api
+    with pytest.raises(api.SbqError) as e:
+        api.Quantifier(device=0, n_gpus=torch.cuda.device_count() + 1)
+    assert e.value.code == api.SBQ_ERR_NO_DEVICE

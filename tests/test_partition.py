@@ -26,6 +26,20 @@ def test_lpt_partition_is_balanced_and_deterministic():
         assert all(np.array_equal(a, c) for a, c in zip(parts, again))
 
 
+def test_c_abi_lpt_equals_the_python_partition(sbq_lib_path):
+    """sbq_partition_lpt (what sbq_upload runs for n_gpus > 1) and partition.lpt_partition (torchrun path) must deal the
+    same loci to the same part, ties included - host-only entry point, no device needed."""
+    from strawberry_b200 import api
+    rng = np.random.default_rng(5)
+    b = synth.human_shaped(n_loci=3000, total_fragments=1_000_000, seed=8)
+    for cost in (partition.locus_cost(b), rng.integers(1, 4, 500), np.full(37, 7), np.zeros(0, np.int64)):
+        for n in (1, 2, 3, 8):
+            owner = api.partition_lpt(cost, n)
+            parts = partition.lpt_partition(cost, n)
+            for p_, idx in enumerate(parts):
+                assert np.array_equal(np.nonzero(owner == p_)[0], idx)
+
+
 def test_take_preserves_loci():
     b = synth.human_shaped(n_loci=200, total_fragments=50_000, seed=9)
     idx = np.array([3, 17, 18, 150, 199])
