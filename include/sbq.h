@@ -187,6 +187,27 @@ typedef struct {
 } sbq_launch_stat;
 int  sbq_get_launch_stats(const sbq_ctx*, sbq_launch_stat* out, int cap);
 
+/* Giant-locus stress input generated ON THE DEVICE from a seed (BASELINE configs[3]: 200 loci x
+ * 1 M single-fragment rows x ~48 compatible isoforms are ~115 GB of CSR that never cross PCIe). The data of a locus is a
+ * pure function of (seed, GLOBAL locus id), so any split of the ids over devices or waves yields the same loci; the
+ * generator is restated on the CPU in strawberry_b200/synth.py::giant_device (bit-exact, tests/test_gpu_synth.py).
+ * Replaces sbq_submit* + sbq_upload: the batch exists in HBM only, sbq_solve / sbq_download / sbq_results follow. */
+typedef struct {
+   uint64_t seed;
+   int32_t  n_loci;            /* loci generated by this call                                                      */
+   const int32_t* locus_ids;   /* their n_loci global ids, or NULL for 0 .. n_loci - 1                              */
+   int64_t  rows_per_locus;    /* every row is one fragment (n_i = 1)                                               */
+   int32_t  iso_lo, iso_hi;    /* T ~ U{iso_lo .. iso_hi}                                                           */
+   double   mean_extra;        /* row degree k ~ 1 + Poisson(mean_extra), capped at min(T, 255)                     */
+} sbq_synth_giant_spec;
+int  sbq_synth_giant(sbq_ctx*, const sbq_synth_giant_spec* spec);
+
+/* Device -> host copy of the resident batch in the sbq_submit_flat layout (any pointer may be NULL); the arrays must hold
+ * n_loci + 1, n_loci + 1, n_row + 1, nnz, nnz, n_row and n_iso elements (sbq_get_stats has the sizes). For tests of
+ * device-generated batches. After a solve, the weights of giant-locus rows come back in the kernel's bank-sorted order. */
+int  sbq_fetch_batch(sbq_ctx*, int64_t* loc_row_off, int64_t* loc_iso_off, int64_t* row_ptr, int32_t* col, double* alpha,
+                     int32_t* count, int32_t* iso_len);
+
 /* Greedy longest-processing-time partition of n loci with the given costs over n_parts devices: loci by descending
  * cost (ties: lower index first) onto the currently lightest part (ties: lower part first). owner[l] receives the part
  * of locus l. Host-only and deterministic - it is what sbq_upload runs for n_gpus > 1 with cost = nnz + rows + isoforms

@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "sbq_submit", "sbq_submit_flat", "sbq_clear", "sbq_validate", "sbq_host_alloc", "sbq_host_free",
     "sbq_upload", "sbq_solve", "sbq_download", "sbq_run", "sbq_fpkm_sum", "sbq_fpkm_sum_to_device",
     "sbq_finalize_tpm", "sbq_results", "sbq_get_stats", "sbq_get_launch_stats", "sbq_em_solve", "sbq_set_plan",
-    "sbq_set_covariates", "sbq_bias_results", "sbq_partition_lpt", "sbq_locus_devices",
+    "sbq_set_covariates", "sbq_bias_results", "sbq_partition_lpt", "sbq_locus_devices", "sbq_synth_giant", "sbq_fetch_batch",
 ]
 
 
@@ -48,6 +48,11 @@ class Locus(ctypes.Structure):
     _fields_ = [("n_iso", ctypes.c_int32), ("n_row", ctypes.c_int32), ("row_ptr", ctypes.c_void_p),
                 ("col", ctypes.c_void_p), ("alpha", ctypes.c_void_p), ("count", ctypes.c_void_p),
                 ("iso_len", ctypes.c_void_p)]
+
+
+class SynthGiantSpec(ctypes.Structure):
+    _fields_ = [("seed", ctypes.c_uint64), ("n_loci", ctypes.c_int32), ("locus_ids", ctypes.c_void_p), ("rows_per_locus", ctypes.c_int64),
+                ("iso_lo", ctypes.c_int32), ("iso_hi", ctypes.c_int32), ("mean_extra", ctypes.c_double)]
 
 
 class Stats(ctypes.Structure):
@@ -105,6 +110,8 @@ def lib():
         L.sbq_bias_results.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.sbq_partition_lpt.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p]
         L.sbq_locus_devices.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.sbq_synth_giant.argtypes = [ctypes.c_void_p, ctypes.POINTER(SynthGiantSpec)]
+        L.sbq_fetch_batch.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 7
         _lib = L
     return _lib
 
@@ -283,6 +290,23 @@ class Quantifier:
         return [dict(kernel=grid.get(buf[i].variant, names[buf[i].kind]) if buf[i].kind == 3 else names[buf[i].kind], cluster_size=buf[i].cluster_size, lanes_per_row=buf[i].lanes_per_row,
                      n_loci=buf[i].n_loci, nnz=buf[i].nnz, ms=buf[i].ms, alg_bytes=buf[i].alg_bytes,
                      frag_iters=buf[i].frag_iters, max_iters=buf[i].max_iters) for i in range(min(n, cap))]
+
+    def synth_giant(self, locus_ids, rows_per_locus, seed=4, iso_lo=500, iso_hi=800, mean_extra=47.0):
+        """Generate giant loci ON THE DEVICE (sbq_synth_giant): replaces submit + upload, the batch lives in HBM only."""
+        ids = _c(locus_ids, np.int32)
+        spec = SynthGiantSpec(int(seed), len(ids), ids.ctypes.data, int(rows_per_locus), int(iso_lo), int(iso_hi), float(mean_extra))
+        self._keepalive = []
+        self._chk(self._L.sbq_synth_giant(self._h, ctypes.byref(spec)))
+
+    def fetch_batch(self):
+        """Device -> host copy of the resident batch (flat layout of include/sbq.h); for tests of device-generated input."""
+        st = self.stats()
+        out = dict(loc_row_off=np.empty(st["n_loci"] + 1, np.int64), loc_iso_off=np.empty(st["n_loci"] + 1, np.int64),
+                   row_ptr=np.empty(st["n_row"] + 1, np.int64), col=np.empty(st["nnz"], np.int32), alpha=np.empty(st["nnz"]),
+                   count=np.empty(st["n_row"], np.int32), iso_len=np.empty(st["n_iso"], np.int32))
+        self._chk(self._L.sbq_fetch_batch(self._h, *[_ptr(out[k]) for k in ("loc_row_off", "loc_iso_off", "row_ptr", "col", "alpha", "count", "iso_len")]))
+        out["total_mapped_reads"] = int(out["count"].sum())
+        return out
 
     def locus_devices(self):
         """device ordinal that solved each queued locus (multi-GPU contexts partition loci by non-zeros)"""

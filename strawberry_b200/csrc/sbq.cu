@@ -27,6 +27,7 @@
 #include "sbq_grid_dual.cuh"
 #include "sbq_bias.cuh"
 #include "sbq_weights.cuh"
+#include "sbq_synth.cuh"
 
 using namespace sbq;
 
@@ -165,7 +166,7 @@ struct sbq_ctx {
    size_t warp_list_off = 0, grid_list_off = 0;
 
    // device
-   DevBuf d_in, d_out, d_lists, d_grid_scratch, d_col16, d_rowrec, d_csc;
+   DevBuf d_in, d_out, d_lists, d_grid_scratch, d_col16, d_rowrec, d_csc, d_synth;
    bool col16_ready = false, grid_tma_ok = false, grid_dual_ok = false;
    std::vector<int64_t> grid_rec_off;            // row-record offset of every two-slot-kernel locus (+ total), list order
    size_t grid_n_dual = 0;                       // the first grid_n_dual entries of grid_list run on the two-slot kernel, the rest on the TMA ring / register-staged kernel
@@ -299,10 +300,20 @@ int cluster_size_for(int64_t nnz) {
 }
 
 // ---- planner: tier per locus, launch classes, work lists sorted by descending size -------------
+// per-locus shape and fragment total from the staged host arrays (while they are still valid)
+void capture_meta_host(sbq_ctx* c) {
+   const int64_t *lro = loc_row_off(c), *lio = loc_iso_off(c), *rp = row_ptr(c);
+   const int32_t* cnt = countp(c);
+   c->meta.resize((size_t)c->n_loci);
+   for (int64_t l = 0; l < c->n_loci; ++l) {
+      int64_t frags = 0;
+      for (int64_t i = lro[l]; i < lro[l + 1]; ++i) frags += cnt[i];
+      c->meta[l] = {rp[lro[l + 1]] - rp[lro[l]], frags, (int32_t)(lro[l + 1] - lro[l]), (int32_t)(lio[l + 1] - lio[l])};
+   }
+}
+
+// works from c->meta only, so that batches that exist only on the device (sbq_synth_giant) are planned the same way
 int plan(sbq_ctx* c) {
-   const int64_t* lro = loc_row_off(c);
-   const int64_t* lio = loc_iso_off(c);
-   const int64_t* rp = row_ptr(c);
    c->warp_list.clear();
    c->grid_list.clear();
    c->classes.clear();
@@ -319,15 +330,9 @@ int plan(sbq_ctx* c) {
    std::vector<LaunchClass> tmp;
    tmp.reserve(20);
    const int64_t grid_min_nnz = 300 * 1000;   // above this a locus is faster on the whole GPU than on a 16-CTA cluster
-   const int32_t* cnt = countp(c);
-   c->meta.resize((size_t)c->n_loci);
    for (int64_t l = 0; l < c->n_loci; ++l) {
-      const int64_t R = lro[l + 1] - lro[l], T = lio[l + 1] - lio[l];
-      const int64_t nnz = rp[lro[l + 1]] - rp[lro[l]];
+      const int64_t R = c->meta[l].R, T = c->meta[l].T, nnz = c->meta[l].nnz;
       nnz_of[l] = nnz;
-      int64_t frags = 0;
-      for (int64_t i = lro[l]; i < lro[l + 1]; ++i) frags += cnt[i];
-      c->meta[l] = {nnz, frags, (int32_t)R, (int32_t)T};
       c->max_iso_all = std::max(c->max_iso_all, (int)T);
       if (T > SBQ_MAX_ISO) return fail(c, SBQ_ERR_UNSUPPORTED, "locus %lld has %lld isoforms (> SBQ_MAX_ISO)", (long long)l, (long long)T);
       int tier;
@@ -382,8 +387,7 @@ int plan(sbq_ctx* c) {
    for (int32_t l : c->grid_list) c->grid_n_dual += dual_locus[l];
    c->grid_rec_off.assign(c->grid_n_dual + 1, 0);
    for (size_t i = 0; i < c->grid_n_dual; ++i) {
-      const int64_t R = lro[c->grid_list[i] + 1] - lro[c->grid_list[i]];
-      c->grid_rec_off[i + 1] = c->grid_rec_off[i] + R + 1;
+      c->grid_rec_off[i + 1] = c->grid_rec_off[i] + c->meta[c->grid_list[i]].R + 1;
    }
    for (auto& lc : tmp) {
       std::sort(lc.loci.begin(), lc.loci.end(), by_size);
@@ -411,6 +415,47 @@ int plan(sbq_ctx* c) {
 }
 
 size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// device arrays of the batch (sizes from c->n_loci / n_row / n_iso / nnz) and of its results; fills c->dp
+int alloc_device(sbq_ctx* c) {
+   // +64 B of slack per array: the giant-locus kernel's 16-byte-granular bulk copies may read a few elements past the end
+   const size_t sz_lro = align_up((c->n_loci + 1) * sizeof(int64_t)), sz_rp = align_up((c->n_row + 1) * sizeof(int64_t) + 64);
+   const size_t sz_col = align_up(c->nnz * sizeof(int32_t) + 64), sz_al = align_up(c->nnz * sizeof(double) + 64);
+   const size_t sz_cnt = align_up(c->n_row * sizeof(int32_t) + 64), sz_il = align_up(c->n_iso * sizeof(int32_t));
+   const size_t in_bytes = 2 * sz_lro + sz_rp + sz_col + sz_al + 2 * sz_cnt + sz_il;
+   const size_t sz_iso_d = align_up(c->n_iso * sizeof(double)), sz_iso_i = align_up(c->n_iso * sizeof(int32_t));
+   const size_t sz_loc_i = align_up(c->n_loci * sizeof(int32_t)), sz_loc_d = align_up(c->n_loci * sizeof(double));
+   const size_t out_bytes = 4 * sz_iso_d + sz_iso_i + 2 * sz_loc_i + sz_loc_d + 256;
+   if (!c->d_in.reserve(in_bytes) || !c->d_out.reserve(out_bytes) || !c->d_lists.reserve(align_up((size_t)c->n_loci * sizeof(int32_t)) + 256))
+      return fail(c, SBQ_ERR_NOMEM, "device allocation failed (%zu MB)", (in_bytes + out_bytes) >> 20);
+
+   char* p = (char*)c->d_in.p;
+   DevParams& dp = c->dp;
+   auto carve = [&](size_t bytes) { char* q = p; p += bytes; return q; };
+   int64_t* d_lro = (int64_t*)carve(sz_lro);
+   int64_t* d_lio = (int64_t*)carve(sz_lro);
+   int64_t* d_rp = (int64_t*)carve(sz_rp);
+   int32_t* d_col = (int32_t*)carve(sz_col);
+   double* d_al = (double*)carve(sz_al);
+   int32_t* d_cnt = (int32_t*)carve(sz_cnt);
+   dp.neff = (int32_t*)carve(sz_cnt);
+   int32_t* d_il = (int32_t*)carve(sz_il);
+   dp.csc = nullptr;   // allocated after the plan, only when the cluster tier has loci
+   dp.loc_row_off = d_lro; dp.loc_iso_off = d_lio; dp.row_ptr = d_rp; dp.col = d_col; dp.alpha = d_al;
+   dp.count = d_cnt; dp.iso_len = d_il;
+   p = (char*)c->d_out.p;
+   dp.theta = (double*)carve(sz_iso_d);
+   dp.fpkm = (double*)carve(sz_iso_d);
+   dp.frac = (double*)carve(sz_iso_d);
+   c->d_tpm = (double*)carve(sz_iso_d);
+   dp.keep = (int32_t*)carve(sz_iso_i);
+   dp.iters = (int32_t*)carve(sz_loc_i);
+   dp.status = (int32_t*)carve(sz_loc_i);
+   dp.locus_fpkm = (double*)carve(sz_loc_d);
+   c->d_fpkm_sum = (double*)carve(256);
+   c->d_lists_p = (int32_t*)c->d_lists.p;
+   return SBQ_SUCCESS;
+}
 
 template <typename K>
 int set_kernel_attrs(sbq_ctx* c, K kernel, size_t smem, bool nonportable) {
@@ -596,7 +641,7 @@ void sbq_destroy(sbq_ctx* c) {
    c->h_lists.release();
    c->r_theta.release(); c->r_fpkm.release(); c->r_frac.release(); c->r_tpm.release();
    c->r_locus_fpkm.release(); c->r_keep.release(); c->r_iters.release(); c->r_status.release();
-   c->d_in.release(); c->d_out.release(); c->d_lists.release(); c->d_grid_scratch.release(); c->d_col16.release(); c->d_rowrec.release(); c->d_csc.release(); c->d_bias.release();
+   c->d_in.release(); c->d_out.release(); c->d_lists.release(); c->d_grid_scratch.release(); c->d_col16.release(); c->d_rowrec.release(); c->d_csc.release(); c->d_synth.release(); c->d_bias.release();
    c->h_cov.release(); c->r_beta.release(); c->r_outer.release();
    c->h_wseg.release(); c->h_wn.release(); c->h_wmask.release(); c->h_wpool.release(); c->h_wlen.release(); c->d_weights.release();
    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -716,42 +761,14 @@ int sbq_upload(sbq_ctx* c) {
    CU(cudaSetDevice(c->device));
    if (c->n_loci == 0) return fail(c, SBQ_ERR_STATE, "nothing submitted");
    if (c->host_released) return fail(c, SBQ_ERR_STATE, "the borrowed batch was released by the previous sbq_upload: sbq_clear and submit again");
-   // +64 B of slack per array: the giant-locus kernel's 16-byte-granular bulk copies may read a few elements past the end
-   const size_t sz_lro = align_up((c->n_loci + 1) * sizeof(int64_t)), sz_rp = align_up((c->n_row + 1) * sizeof(int64_t) + 64);
-   const size_t sz_col = align_up(c->nnz * sizeof(int32_t) + 64), sz_al = align_up(c->nnz * sizeof(double) + 64);
-   const size_t sz_cnt = align_up(c->n_row * sizeof(int32_t) + 64), sz_il = align_up(c->n_iso * sizeof(int32_t));
-   const size_t in_bytes = 2 * sz_lro + sz_rp + sz_col + sz_al + 2 * sz_cnt + sz_il;
-   const size_t sz_iso_d = align_up(c->n_iso * sizeof(double)), sz_iso_i = align_up(c->n_iso * sizeof(int32_t));
-   const size_t sz_loc_i = align_up(c->n_loci * sizeof(int32_t)), sz_loc_d = align_up(c->n_loci * sizeof(double));
-   const size_t out_bytes = 4 * sz_iso_d + sz_iso_i + 2 * sz_loc_i + sz_loc_d + 256;
-   if (!c->d_in.reserve(in_bytes) || !c->d_out.reserve(out_bytes) || !c->d_lists.reserve(align_up((size_t)c->n_loci * sizeof(int32_t)) + 256))
-      return fail(c, SBQ_ERR_NOMEM, "device allocation failed (%zu MB)", (in_bytes + out_bytes) >> 20);
-
-   char* p = (char*)c->d_in.p;
+   {
+      const int rc = alloc_device(c);
+      if (rc) return rc;
+   }
    DevParams& dp = c->dp;
-   auto carve = [&](size_t bytes) { char* q = p; p += bytes; return q; };
-   int64_t* d_lro = (int64_t*)carve(sz_lro);
-   int64_t* d_lio = (int64_t*)carve(sz_lro);
-   int64_t* d_rp = (int64_t*)carve(sz_rp);
-   int32_t* d_col = (int32_t*)carve(sz_col);
-   double* d_al = (double*)carve(sz_al);
-   int32_t* d_cnt = (int32_t*)carve(sz_cnt);
-   dp.neff = (int32_t*)carve(sz_cnt);
-   int32_t* d_il = (int32_t*)carve(sz_il);
-   dp.csc = nullptr;   // allocated after the plan, only when the cluster tier has loci
-   dp.loc_row_off = d_lro; dp.loc_iso_off = d_lio; dp.row_ptr = d_rp; dp.col = d_col; dp.alpha = d_al;
-   dp.count = d_cnt; dp.iso_len = d_il;
-   p = (char*)c->d_out.p;
-   dp.theta = (double*)carve(sz_iso_d);
-   dp.fpkm = (double*)carve(sz_iso_d);
-   dp.frac = (double*)carve(sz_iso_d);
-   c->d_tpm = (double*)carve(sz_iso_d);
-   dp.keep = (int32_t*)carve(sz_iso_i);
-   dp.iters = (int32_t*)carve(sz_loc_i);
-   dp.status = (int32_t*)carve(sz_loc_i);
-   dp.locus_fpkm = (double*)carve(sz_loc_d);
-   c->d_fpkm_sum = (double*)carve(256);
-   c->d_lists_p = (int32_t*)c->d_lists.p;
+   int64_t *d_lro = const_cast<int64_t*>(dp.loc_row_off), *d_lio = const_cast<int64_t*>(dp.loc_iso_off), *d_rp = const_cast<int64_t*>(dp.row_ptr);
+   int32_t *d_col = const_cast<int32_t*>(dp.col), *d_cnt = const_cast<int32_t*>(dp.count), *d_il = const_cast<int32_t*>(dp.iso_len);
+   double* d_al = const_cast<double*>(dp.alpha);
 
    cudaStream_t st = c->stream;
    CU(cudaEventRecord(c->ev[0], st));
@@ -764,8 +781,9 @@ int sbq_upload(sbq_ctx* c) {
    }
    if (c->n_row) CU(cudaMemcpyAsync(d_cnt, countp(c), c->n_row * sizeof(int32_t), cudaMemcpyHostToDevice, st));
    CU(cudaMemcpyAsync(d_il, iso_lenp(c), c->n_iso * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-   // the tier plan (O(loci) on the host) is made while the DMA engine moves the batch
+   // the tier plan (O(loci + rows) on the host) is made while the DMA engine moves the batch
    {
+      capture_meta_host(c);
       const int rc = plan(c);
       if (rc) {
          cudaStreamSynchronize(st);
@@ -1208,6 +1226,124 @@ int sbq_submit_deferred(sbq_ctx* c, const sbq_table* const* tables, int64_t n_ta
       }
       c->deferred = 1;
    }
+   return SBQ_SUCCESS;
+}
+
+int sbq_synth_giant(sbq_ctx* c, const sbq_synth_giant_spec* sp) {
+   if (!c || !sp || sp->n_loci < 1 || sp->rows_per_locus < 1 || sp->iso_lo < 1 || sp->iso_hi < sp->iso_lo || sp->iso_hi > SBQ_MAX_ISO ||
+       !(sp->mean_extra >= 0) || sp->mean_extra > 200.0)
+      return SBQ_ERR_INVALID;
+   if (c->multi) return fail(c, SBQ_ERR_UNSUPPORTED, "sbq_synth_giant is per device: give every device of a partition its own locus ids");
+   if (c->cfg.bias_mode) return fail(c, SBQ_ERR_UNSUPPORTED, "sbq_synth_giant generates no covariates");
+   std::lock_guard<std::mutex> lk(c->mu);
+   CU(cudaSetDevice(c->device));
+   reset_batch(c);
+   const int L = sp->n_loci;
+   const int64_t rows = sp->rows_per_locus, n_row = (int64_t)L * rows;
+   // per-locus keys and T on the host (same hash as the device code), Poisson CDF by the exactly reproducible recurrence
+   std::vector<SynthLocus> hl((size_t)L);
+   std::vector<int64_t> h_lro((size_t)L + 1), h_lio((size_t)L + 1, 0);
+   for (int l = 0; l < L; ++l) {
+      const uint64_t id = sp->locus_ids ? (uint64_t)(uint32_t)sp->locus_ids[l] : (uint64_t)l;
+      hl[l].key_deg = synth_key(sp->seed, id, 1);
+      hl[l].key_ent = synth_key(sp->seed, id, 2);
+      hl[l].key_len = synth_key(sp->seed, id, 3);
+      hl[l].T = sp->iso_lo + (int32_t)(sm64(synth_key(sp->seed, id, 0)) % (uint64_t)(sp->iso_hi - sp->iso_lo + 1));
+      hl[l].pad = 0;
+      h_lro[l] = (int64_t)l * rows;
+      h_lio[l + 1] = h_lio[l] + hl[l].T;
+   }
+   h_lro[L] = n_row;
+   double cdf[SYN_CDF];
+   {
+      double pk = std::exp(-sp->mean_extra);
+      cdf[0] = pk;
+      for (int k = 1; k < SYN_CDF; ++k) {
+         pk = pk * (sp->mean_extra / (double)k);
+         cdf[k] = cdf[k - 1] + pk;
+      }
+   }
+   const int n_scan = (int)((n_row + SYN_SCAN_BLOCK - 1) / SYN_SCAN_BLOCK);
+   const size_t b_loci = align_up(L * sizeof(SynthLocus)), b_cdf = align_up(sizeof cdf), b_deg = align_up((size_t)n_row), b_sum = align_up((size_t)n_scan * 8 + 8);
+   if (!c->d_synth.reserve(b_loci + b_cdf + b_deg + b_sum + 256)) return fail(c, SBQ_ERR_NOMEM, "device allocation failed (generator scratch)");
+   char* q = (char*)c->d_synth.p;
+   SynthLocus* d_loci = (SynthLocus*)q; q += b_loci;
+   double* d_cdf = (double*)q; q += b_cdf;
+   unsigned char* d_deg = (unsigned char*)q; q += b_deg;
+   long long* d_bsum = (long long*)q; q += b_sum;
+   unsigned long long* d_total = (unsigned long long*)q;
+   cudaStream_t st = c->stream;
+   CU(cudaEventRecord(c->ev[0], st));
+   CU(cudaMemcpyAsync(d_loci, hl.data(), L * sizeof(SynthLocus), cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(d_cdf, cdf, sizeof cdf, cudaMemcpyHostToDevice, st));
+   CU(cudaMemsetAsync(d_total, 0, 8, st));
+   const int nb = c->prop.multiProcessorCount * 8;
+   synth_degree_kernel<<<nb, 256, 0, st>>>(d_loci, L, rows, d_cdf, d_deg, d_total);
+   CU(cudaGetLastError());
+   unsigned long long total = 0;
+   CU(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, st));
+   CU(cudaStreamSynchronize(st));
+   c->n_loci = L; c->n_row = n_row; c->n_iso = h_lio[L]; c->nnz = (int64_t)total;
+   {
+      const int rc = alloc_device(c);
+      if (rc) { reset_batch(c); return rc; }
+   }
+   DevParams& dp = c->dp;
+   CU(cudaMemcpyAsync(const_cast<int64_t*>(dp.loc_row_off), h_lro.data(), (L + 1) * 8, cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(const_cast<int64_t*>(dp.loc_iso_off), h_lio.data(), (L + 1) * 8, cudaMemcpyHostToDevice, st));
+   synth_scan_sums_kernel<<<n_scan, 1024, 0, st>>>(d_deg, n_row, d_bsum);
+   synth_scan_blocks_kernel<<<1, 1024, 0, st>>>(d_bsum, n_scan);
+   synth_scan_fill_kernel<<<n_scan, 1024, 0, st>>>(d_deg, n_row, d_bsum, const_cast<int64_t*>(dp.row_ptr), const_cast<int32_t*>(dp.count));
+   synth_fill_kernel<<<nb, 256, 0, st>>>(d_loci, L, rows, dp.row_ptr, const_cast<int32_t*>(dp.col), const_cast<double*>(dp.alpha));
+   synth_len_kernel<<<std::min(L, 1024), 256, 0, st>>>(d_loci, L, dp.loc_iso_off, const_cast<int32_t*>(dp.iso_len));
+   CU(cudaGetLastError());
+   // per-locus non-zeros for the planner: row_ptr at the locus boundaries (one strided copy)
+   std::vector<int64_t> bound((size_t)L + 1);
+   CU(cudaMemcpy2DAsync(bound.data(), 8, dp.row_ptr, (size_t)rows * 8, 8, (size_t)L + 1, cudaMemcpyDeviceToHost, st));
+   CU(cudaStreamSynchronize(st));
+   c->meta.resize((size_t)L);
+   for (int l = 0; l < L; ++l) c->meta[l] = {bound[l + 1] - bound[l], rows, (int32_t)rows, hl[l].T};
+   if (rows > INT32_MAX) return fail(c, SBQ_ERR_INVALID, "rows_per_locus too large");
+   {
+      const int rc = plan(c);
+      if (rc) { reset_batch(c); return rc; }
+   }
+   if (c->h_lists.n) CU(cudaMemcpyAsync(c->d_lists_p, c->h_lists.p, c->h_lists.n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+   if (!c->classes.empty()) {
+      if (!c->d_csc.reserve(align_up(c->nnz * 4 + 16))) return fail(c, SBQ_ERR_NOMEM, "device allocation failed (transposed-index scratch)");
+      dp.csc = (unsigned*)c->d_csc.p;
+   }
+   CU(cudaEventRecord(c->ev[1], st));
+   CU(cudaStreamSynchronize(st));
+   float ms = 0;
+   CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+   c->stats.upload_ms = ms;   // generation time stands in for the upload
+   c->stats.h2d_bytes = 0;
+   c->stats.n_loci = c->n_loci; c->stats.n_row = c->n_row; c->stats.n_iso = c->n_iso; c->stats.nnz = c->nnz;
+   c->stats.weights_ms = 0.0;
+   c->deferred = 2;
+   c->host_released = true;   // the batch exists on the device only
+   c->resident = true;
+   c->col16_ready = false;
+   c->solved = c->downloaded = false;
+   return SBQ_SUCCESS;
+}
+
+int sbq_fetch_batch(sbq_ctx* c, int64_t* loc_row_off_, int64_t* loc_iso_off_, int64_t* row_ptr_, int32_t* col, double* alpha, int32_t* count, int32_t* iso_len) {
+   if (!c) return SBQ_ERR_INVALID;
+   if (c->multi) return fail(c, SBQ_ERR_UNSUPPORTED, "sbq_fetch_batch is single-device");
+   std::lock_guard<std::mutex> lk(c->mu);
+   CU(cudaSetDevice(c->device));
+   if (!c->resident) return fail(c, SBQ_ERR_STATE, "sbq_fetch_batch before sbq_upload / sbq_synth_giant");
+   cudaStream_t st = c->stream;
+   if (loc_row_off_) CU(cudaMemcpyAsync(loc_row_off_, c->dp.loc_row_off, (c->n_loci + 1) * 8, cudaMemcpyDeviceToHost, st));
+   if (loc_iso_off_) CU(cudaMemcpyAsync(loc_iso_off_, c->dp.loc_iso_off, (c->n_loci + 1) * 8, cudaMemcpyDeviceToHost, st));
+   if (row_ptr_) CU(cudaMemcpyAsync(row_ptr_, c->dp.row_ptr, (c->n_row + 1) * 8, cudaMemcpyDeviceToHost, st));
+   if (col) CU(cudaMemcpyAsync(col, c->dp.col, c->nnz * 4, cudaMemcpyDeviceToHost, st));
+   if (alpha) CU(cudaMemcpyAsync(alpha, c->dp.alpha, c->nnz * 8, cudaMemcpyDeviceToHost, st));
+   if (count) CU(cudaMemcpyAsync(count, c->dp.count, c->n_row * 4, cudaMemcpyDeviceToHost, st));
+   if (iso_len) CU(cudaMemcpyAsync(iso_len, c->dp.iso_len, c->n_iso * 4, cudaMemcpyDeviceToHost, st));
+   CU(cudaStreamSynchronize(st));
    return SBQ_SUCCESS;
 }
 

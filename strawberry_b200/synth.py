@@ -114,6 +114,80 @@ def giant(n_loci=2, rows_per_locus=200_000, seed=4, iso_lo=500, iso_hi=800, mean
                           rows_per_locus=rows_per_locus))
 
 
+DEVICE_GENERATOR_VERSION = "sbq-synth-dev-1"
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _sm64(x):
+    """splitmix64 finaliser on uint64 arrays (wrapping arithmetic), as strawberry_b200/csrc/sbq_synth.cuh::sm64."""
+    x = np.asarray(x, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def _synth_key(seed, ids, stream):
+    with np.errstate(over="ignore"):
+        return _sm64(_sm64(np.uint64(seed) ^ np.uint64(0x5851F42D4C957F2D)) + np.uint64(4) * np.asarray(ids, np.uint64) + np.uint64(stream))
+
+
+def _synth_u(h):
+    return (h >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def giant_device_iso(seed, ids, iso_lo=500, iso_hi=800):
+    """T of the device-generated giant loci `ids` (host-side hash only)."""
+    return (iso_lo + (_sm64(_synth_key(seed, ids, 0)) % np.uint64(iso_hi - iso_lo + 1)).astype(np.int64)).astype(np.int64)
+
+
+def giant_device(locus_ids, rows_per_locus, seed=4, iso_lo=500, iso_hi=800, mean_extra=47.0):
+    """numpy restatement of the ON-DEVICE giant-locus generator (sbq_synth_giant, csrc/sbq_synth.cuh): bit-equal row
+    pointers, columns, weights, counts and lengths. A locus is a pure function of (seed, global locus id): T ~ U{iso_lo..iso_hi};
+    every row is one fragment with k ~ 1 + Poisson(mean_extra) (CDF inversion, capped at min(T, 255)) compatible isoforms drawn
+    by stratified sampling; alpha = (1 + u) 2^-(6 + e), e ~ U{0..7} (piecewise log-uniform on [1.2e-4, 3.1e-2), exact in fp64)."""
+    import math
+    ids = np.asarray(locus_ids, dtype=np.int64)
+    L, rows = len(ids), int(rows_per_locus)
+    T = giant_device_iso(seed, ids, iso_lo, iso_hi)
+    cdf = np.empty(255)
+    pk = math.exp(-mean_extra)
+    cdf[0] = pk
+    for k in range(1, 255):
+        pk = pk * (mean_extra / float(k))
+        cdf[k] = cdf[k - 1] + pk
+    i = np.arange(rows, dtype=np.uint64)
+    degs, cols, alphas, lens = [], [], [], []
+    with np.errstate(over="ignore"):
+        for l in range(L):
+            t = int(T[l])
+            u = _synth_u(_sm64(_synth_key(seed, ids[l], 1) + i))
+            k = 1 + np.minimum(np.searchsorted(cdf, u, side="right"), 254)
+            k = np.minimum(k, min(t, 255)).astype(np.int64)
+            row_of = np.repeat(np.arange(rows, dtype=np.int64), k)
+            start = np.concatenate([[0], np.cumsum(k)])
+            m = np.arange(int(start[-1]), dtype=np.int64) - start[row_of]
+            kk = k[row_of]
+            v = _sm64(_synth_key(seed, ids[l], 2) + (np.uint64(256) * row_of.astype(np.uint64) + m.astype(np.uint64)))
+            lo, hi = (m * t) // kk, ((m + 1) * t) // kk
+            cols.append((lo + (_synth_u(v) * (hi - lo).astype(np.float64)).astype(np.int64)).astype(np.int32))
+            w = _sm64(v)
+            alphas.append(np.ldexp(1.0 + _synth_u(w), -(6 + (w & np.uint64(7)).astype(np.int64)).astype(np.int32)))
+            degs.append(k)
+            lens.append((400 + (_sm64(_synth_key(seed, ids[l], 3) + np.arange(t, dtype=np.uint64)) % np.uint64(7601)).astype(np.int64)).astype(np.int32))
+    k_all = np.concatenate(degs) if L else np.zeros(0, np.int64)
+    row_ptr = np.zeros(L * rows + 1, np.int64)
+    np.cumsum(k_all, out=row_ptr[1:])
+    loc_iso_off = np.zeros(L + 1, np.int64)
+    np.cumsum(T, out=loc_iso_off[1:])
+    return dict(loc_row_off=np.arange(L + 1, dtype=np.int64) * rows, loc_iso_off=loc_iso_off, row_ptr=row_ptr,
+                col=np.concatenate(cols), alpha=np.concatenate(alphas), count=np.ones(L * rows, np.int32),
+                iso_len=np.concatenate(lens), total_mapped_reads=int(L * rows),
+                meta=dict(generator=DEVICE_GENERATOR_VERSION, kind="giant_device", seed=seed, locus_ids=ids.tolist(),
+                          rows_per_locus=rows))
+
+
 def collapsed_giant(n_loci=1, rows=20000, n_iso=500, density=0.05, seed=4):
     """Config 4's 'collapsed-faithful' variant the dense reference can still run."""
     rng = np.random.default_rng(seed)
