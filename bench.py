@@ -1,17 +1,27 @@
 #!/usr/bin/env python
 """bench.py - the reference's headline metric on B200: fragments*EM-iters/sec (and wall time to
-converge) of the per-locus Latent-Class-Model EM on a synthetic 10M-fragment, ~20k-locus human-shaped
-batch (BASELINE.json configs[1]; generator strawberry_b200.synth.human_shaped, seed 2).
+converge) of the per-locus Latent-Class-Model EM on synthetic 10M-fragment, ~20k-locus human-shaped
+batches (BASELINE.json configs[1]; generator strawberry_b200.synth.human_shaped, seeds 2, 3, ...).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A step = one pass of the hot path (EM to convergence + FPKM/frac/filter epilogue + TPM denominator) over
-the rank's batch. `value` is timed with the batch resident in HBM (CUDA events inside libsbq on the
-stream the kernels run on); `e2e` is the same work through the public host-buffer call sbq_run from
-page-locked host arrays, H2D and D2H inside the timed region. N > 1: weak scaling - every rank owns a
-full copy of the batch (seed 2); loci are independent so there is no data-path collective, only the scalar
-TPM-denominator all-reduce (NCCL) per step.
+the job. `value` is timed with the loci resident in HBM (CUDA events inside libsbq on the stream the
+kernels run on); `e2e` is the same work through the public host-buffer calls from page-locked host
+arrays, H2D and D2H inside the timed region.
+
+N > 1 runs the path north_star describes: ONE job is partitioned over the N ranks by non-zeros (greedy
+LPT, strawberry_b200.partition), every rank solves its own loci, and the only collective is the scalar
+all-reduce of the TPM denominator (NCCL). Three legs, all through that partition:
+  headline (weak scaling)  the job is N human-shaped batches pooled (seeds 2 .. N+1, 20000 N loci):
+                           per-GPU work is fixed as N grows; value = fragment-iters of the whole job /
+                           max-over-ranks time.
+  strong                   ONE seed-2 batch (10 M fragments) split over N ranks, with a bitwise check of
+                           every rank's theta / FPKM / frac against the unpartitioned solve.
+  giant                    BASELINE configs[3]: 200 loci x 1 M single-fragment rows x ~48 non-zeros
+                           (~115 GB of CSR), GENERATED ON THE DEVICE from the seed (sbq_synth_giant),
+                           split over N ranks, solved in waves that fit HBM.
 """
 import argparse
 import json
@@ -173,9 +183,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-giant", action="store_true", help="skip the giant-locus roofline leg")
+    ap.add_argument("--no-giant", action="store_true", help="skip the giant-locus leg (BASELINE configs[3])")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (N > 1)")
     ap.add_argument("--giant-rows", type=int, default=1_000_000)
-    ap.add_argument("--giant-loci", type=int, default=2)
+    ap.add_argument("--giant-loci", type=int, default=200)
+    ap.add_argument("--giant-wave", type=int, default=25, help="giant loci resident at once per GPU (~0.7 GB each)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -189,7 +201,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from strawberry_b200 import api, synth
+    from strawberry_b200 import api, partition, synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
@@ -198,11 +210,6 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    # ---- workload: BASELINE configs[1], one full batch per rank (weak scaling)
-    batch = synth.human_shaped(seed=2)   # the same 10M-fragment batch on every rank: identical work per GPU
-    total_reads = batch["total_mapped_reads"]
-    pinned = api.pinned_batch(batch)
-    q = api.Quantifier(device=local_rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     gsum = torch.zeros(1, dtype=torch.float64, device=dev)
 
@@ -211,7 +218,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def tpm_exchange():
+    def reduce_max(*vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def reduce_sum(*vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(x) for x in t]
+
+    def tpm_exchange(q):
         """the path's only exchange step: sum of FPKM over all ranks (src/alignments.cpp:1821-1824)"""
         if world > 1:
             q.fpkm_sum_to_device(gsum.data_ptr())
@@ -220,139 +239,226 @@ def main():
         else:
             q.finalize_tpm(q.fpkm_sum())
 
-    def resident_step():
-        flush.fill_(1)               # L2 flush between timed iterations (not timed: events live inside sbq_solve)
-        torch.cuda.synchronize()
-        q.solve(total_reads)
-        tpm_exchange()
-        return q.stats()["solve_ms"]
+    def timed_legs(q, pinned, total_reads, steps, warmup):
+        """resident leg (per-step solve_ms from CUDA events inside libsbq) and end-to-end leg (host buffers, wall clock)."""
+        def resident_step():
+            flush.fill_(1)               # L2 flush between timed iterations (not timed: events live inside sbq_solve)
+            torch.cuda.synchronize()
+            q.solve(total_reads)
+            tpm_exchange(q)
+            return q.stats()["solve_ms"]
 
-    def e2e_step():
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
+        def e2e_step():
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            q.clear()
+            q.submit_flat(pinned)        # page-locked arrays are used in place
+            q.upload()
+            q.solve(total_reads)
+            tpm_exchange(q)
+            q.download()
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0
+
         q.clear()
-        q.submit_flat(pinned)        # page-locked arrays are used in place
+        q.submit_flat(pinned)
         q.upload()
-        q.solve(total_reads)
-        tpm_exchange()
+        for _ in range(warmup):
+            resident_step()
+        barrier()
+        t0 = time.perf_counter()
+        step_ms = [resident_step() for _ in range(steps)]
+        barrier()
+        wall = time.perf_counter() - t0
         q.download()
-        torch.cuda.synchronize()
-        return time.perf_counter() - t0
+        st, launches, res = q.stats(), q.launch_stats(), q.results()
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        e2e_s = [e2e_step() for _ in range(steps)]
+        barrier()
+        return dict(ms=float(np.mean(step_ms)), e2e_s=float(np.mean(e2e_s)), wall=wall, st=st, st_e2e=q.stats(), launches=launches, res=res)
 
-    # ---- device-resident leg ("value")
-    q.submit_flat(pinned)
-    q.upload()
-    for _ in range(args.warmup):
-        resident_step()
-    barrier()
+    # ---- the job: N human-shaped batches pooled, LPT-partitioned over the N ranks by non-zeros (weak scaling)
+    seeds = list(range(2, 2 + world))
+    job = synth.concat([synth.human_shaped(seed=s_) for s_ in seeds]) if world > 1 else synth.human_shaped(seed=2)
+    total_reads = job["total_mapped_reads"]
+    parts = partition.lpt_partition(partition.locus_cost(job), world)
+    mine, _ = partition.take(job, parts[rank]) if world > 1 else (job, None)
+    pinned = api.pinned_batch(mine)
+    q = api.Quantifier(device=local_rank)
+
     clk = ClockSampler(local_rank)
-    clk.__enter__()                      # sampled over both timed legs (resident + end-to-end)
+    clk.__enter__()                      # sampled over the timed legs of the headline
     t_wall0 = time.perf_counter()
-    step_ms = [resident_step() for _ in range(args.steps)]
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    q.download()
-    st = q.stats()
-    launches = q.launch_stats()
-    res = q.results()
-    frag_iters = st["frag_iters"]
-    ms_local = float(np.mean(step_ms))
-
-    # ---- end-to-end leg (host buffers through the public call)
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    e2e_s = [e2e_step() for _ in range(args.steps)]
-    barrier()
+    hd = timed_legs(q, pinned, total_reads, args.steps, args.warmup)
     clk.__exit__(None, None, None)
-    st_e2e = q.stats()
-    e2e_local = float(np.mean(e2e_s))
+    st, launches, res = hd["st"], hd["launches"], hd["res"]
+    ms_per_step, e2e_per_step = reduce_max(hd["ms"], hd["e2e_s"])
+    total_frag_iters, total_alg, total_launches = reduce_sum(st["frag_iters"], st["alg_bytes"], st["kernel_launches"])
+    em_ms_max, = reduce_max(st["em_ms"])
+    status_counts = reduce_sum(*[float(x) for x in np.bincount(res["status"], minlength=4)])
 
-    # ---- max over ranks, whole-job aggregate
-    agg = torch.tensor([ms_local, e2e_local], dtype=torch.float64, device=dev)
-    tot = torch.tensor([float(frag_iters)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(agg, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms_per_step, e2e_per_step = float(agg[0]), float(agg[1])
-    total_frag_iters = float(tot[0])
-
-    # ---- roofline. The EM kernels of a step (one warp-tier launch + one launch per cluster size) run concurrently on
-    # separate streams, so the phase is timed as a whole with CUDA events on the context's main stream (em_ms) and
-    # every launch also carries its own event pair on its own stream (launches[]). `kernel` names the launch with
-    # the most algorithmic bytes.
+    # ---- roofline of the headline step. The EM kernels of a step (one warp-tier launch + one launch per cluster size) run
+    # concurrently on separate streams, so the phase is timed as a whole with CUDA events on the context's main stream (em_ms)
+    # and every launch also carries its own event pair on its own stream (launches[]). `kernel` names the launch with the most
+    # algorithmic bytes on rank 0.
     peak, peak_src = load_peaks()
     dom = max(launches, key=lambda r: r["alg_bytes"])
     achieved = st["alg_bytes"] / (st["em_ms"] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "kernel": f"{dom['kernel']} (cluster_size={dom['cluster_size']}) + {len(launches) - 1} concurrent EM launches",
-                "kernel_ms": st["em_ms"], "alg_bytes_per_launch": st["alg_bytes"], "peak_source": peak_src,
-                "note": "the 58 MB CSR of the batch is read from HBM once and then lives in shared memory (cluster tier) / L1 (warp tier) for up "
-                        "to 1000 sequential EM iterations, so this step is bound by per-iteration latency of its longest loci, not by HBM; "
-                        "roofline_giant is the HBM-bound kernel of this path",
+                "kernel_ms": st["em_ms"], "alg_bytes_per_launch": st["alg_bytes"], "peak_source": peak_src, "rank": 0,
+                "note": "per GPU (rank 0). The CSR of the rank's loci is read from HBM once and then lives in shared memory (cluster tier) / L1 (warp tier) "
+                        "for up to 1000 sequential EM iterations, so this step is bound by per-iteration latency of its longest loci, not by HBM "
+                        "(DRAM traffic of the phase is a few tens of MB: traffic is not meaningful here); the HBM-bound kernel of this path is the "
+                        "giant-locus one, see `giant.roofline`",
                 "launches": [{k: r[k] for k in ("kernel", "cluster_size", "n_loci", "nnz", "ms", "alg_bytes", "max_iters")} for r in launches]}
 
     line = {"metric": METRIC, "value": total_frag_iters / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[1]: synthetic 10M-fragment paired-end human-shaped loci (20000 loci), quantification only; one such batch per GPU",
-                       "generator": synth.GENERATOR_VERSION, "seed": 2, "loci_per_gpu": st["n_loci"], "rows_per_gpu": st["n_row"],
-                       "isoforms_per_gpu": st["n_iso"], "nnz_per_gpu": st["nnz"], "fragments_per_gpu": int(batch["count"].sum()),
-                       "em_iters_total_per_gpu": st["em_iters_total"], "max_iter": 1000, "theta_tol": 1e-2,
-                       "tiers": {"warp": st["loci_warp"], "cluster": st["loci_cta"], "grid": st["loci_grid"]},
-                       "l2": "flushed between timed iterations (256 MiB fill)", "parallelism": f"loci x{world}"},
+            "config": {"workload": "configs[1]: synthetic 10M-fragment paired-end human-shaped loci (20000 loci), quantification only"
+                                   + ("" if world == 1 else f"; {world} such batches (seeds {seeds[0]}..{seeds[-1]}) pooled into one job of {20000 * world} loci and "
+                                                            f"LPT-partitioned by non-zeros over the {world} GPUs (one scalar NCCL all-reduce per step)"),
+                       "generator": synth.GENERATOR_VERSION, "seeds": seeds, "loci_total": int(len(job["loc_row_off"]) - 1),
+                       "fragments_total": int(job["count"].sum()), "nnz_total": int(job["row_ptr"][-1]),
+                       "loci_rank0": st["n_loci"], "rows_rank0": st["n_row"], "isoforms_rank0": st["n_iso"], "nnz_rank0": st["nnz"],
+                       "em_iters_total_rank0": st["em_iters_total"], "max_iter": 1000, "theta_tol": 1e-2,
+                       "tiers_rank0": {"warp": st["loci_warp"], "cluster": st["loci_cta"], "grid": st["loci_grid"]},
+                       "l2": "flushed between timed iterations (256 MiB fill)", "parallelism": f"loci partitioned x{world} (LPT by nnz)"},
             "wall_ms_to_converge": ms_per_step,
             "e2e": {"value": total_frag_iters / e2e_per_step, "unit": UNIT, "ms_per_step": e2e_per_step * 1e3,
-                    "h2d_bytes_per_step": st_e2e["h2d_bytes"], "d2h_bytes_per_step": st_e2e["d2h_bytes"],
-                    "stages_ms": {"upload": st_e2e["upload_ms"], "solve": st_e2e["solve_ms"], "download": st_e2e["download_ms"]}},
-            "gpu_launches": int((st["kernel_launches"]) * args.steps),
-            "timed_region_wall_s": t_wall,
+                    "h2d_bytes_per_step": int(reduce_sum(hd["st_e2e"]["h2d_bytes"])[0]), "d2h_bytes_per_step": int(reduce_sum(hd["st_e2e"]["d2h_bytes"])[0]),
+                    "stages_ms_rank0": {"upload": hd["st_e2e"]["upload_ms"], "solve": hd["st_e2e"]["solve_ms"], "download": hd["st_e2e"]["download_ms"]}},
+            "gpu_launches": int(total_launches * args.steps),
+            "timed_region_wall_s": hd["wall"],
             "roofline": roofline,
             "clocks": clk.summary(),
-            "statuses": {k: int(v) for k, v in zip(("ok", "iter_cap", "zero_denom", "no_rows"), np.bincount(res["status"], minlength=4))}}
+            "statuses": {k: int(v) for k, v in zip(("ok", "iter_cap", "zero_denom", "no_rows"), status_counts)}}
+
+    # ---- strong scaling: ONE seed-2 batch split over the N ranks, bitwise check against the unpartitioned solve
+    if world > 1 and not args.no_strong:
+        try:
+            one = job if world == 1 else synth.human_shaped(seed=2)
+            q.clear()
+            q.submit_flat(one)
+            q.run(one["total_mapped_reads"])
+            full = q.results()                                   # the 1-GPU answer, computed on every rank
+            sparts = partition.lpt_partition(partition.locus_cost(one), world)
+            sub, isos = partition.take(one, sparts[rank])
+            sd = timed_legs(q, api.pinned_batch(sub), one["total_mapped_reads"], args.steps, args.warmup)
+            r = sd["res"]
+            bad = sum(int(not np.array_equal(r[k], full[k][isos], equal_nan=True)) for k in ("theta", "fpkm", "frac", "keep"))
+            bad += int(not np.array_equal(r["iters"], full["iters"][sparts[rank]])) + int(not np.array_equal(r["status"], full["status"][sparts[rank]]))
+            tpm_dev = float(np.nanmax(np.abs(r["tpm"] - full["tpm"][isos]) / np.maximum(np.abs(full["tpm"][isos]), 1e-300))) if len(isos) else 0.0
+            s_ms, s_e2e, tpm_dev = reduce_max(sd["ms"], sd["e2e_s"], tpm_dev)
+            s_fi, s_bad = reduce_sum(sd["st"]["frag_iters"], bad)
+            nnz_rank = reduce_max(float(sd["st"]["nnz"]))[0]
+            big = int(np.argmax(partition.locus_cost(one)))
+            line["strong"] = {"scaling": "strong", "workload": "configs[1]: ONE seed-2 batch (20000 loci, 10M fragments) LPT-partitioned over the ranks",
+                              "n_gpus": world, "value": s_fi / (s_ms * 1e-3), "unit": UNIT, "ms_per_step": s_ms,
+                              "e2e_ms_per_step": s_e2e * 1e3, "e2e_value": s_fi / s_e2e,
+                              "partition_invariance": {"arrays_differing_bitwise": int(s_bad), "checked": "theta, fpkm, frac, keep, iters, status of every rank's loci vs the 1-GPU solve",
+                                                       "tpm_max_rel_dev": tpm_dev, "tpm_note": "TPM divides by a sum taken in a different order (NCCL all-reduce of per-rank sums)"},
+                              "max_nnz_per_rank": int(nnz_rank),
+                              "floor_note": f"a locus is never split across GPUs: the largest locus ({int(partition.locus_cost(one)[big])} cost units, "
+                                            f"{int(full['iters'][big])} EM iterations) bounds the step from below"}
+        except Exception as e:
+            line["strong"] = {"error": repr(e)}
+
+    # ---- giant-locus leg: BASELINE configs[3], generated on the device, partitioned over the ranks, solved in waves
+    if not args.no_giant:
+        try:
+            line["giant"] = giant_leg(args, api, partition, synth, local_rank, rank, world, flush, reduce_max, reduce_sum, barrier, dist, peak, peak_src)
+        except Exception as e:   # the headline line must still be printed
+            line["giant"] = {"error": repr(e)}
+        if "roofline" in line.get("giant", {}):
+            line["roofline_giant"] = line["giant"]["roofline"]
 
     if rank == 0:
-        # ---- giant-locus leg: the HBM-bound multi-CTA kernel (BASELINE configs[3] shape, scaled to fit a short run)
-        if not args.no_giant:
-            try:
-                gb = synth.giant(n_loci=args.giant_loci, rows_per_locus=args.giant_rows, seed=4)
-                qg = api.Quantifier(device=local_rank)
-                qg.submit_flat(gb)
-                qg.upload()
-                g_ms, g_bytes = [], 0
-                for i in range(1 + 3):
-                    flush.fill_(1)
-                    torch.cuda.synchronize()
-                    qg.solve(gb["total_mapped_reads"])
-                    if i:
-                        g_ms.append(qg.stats()["grid_em_ms"])
-                qg.finalize_tpm(qg.fpkm_sum())
-                qg.download()
-                gst = qg.stats()
-                g_kernel = next((r["kernel"] for r in qg.launch_stats() if r["kernel"].startswith("em_grid")), "em_grid_kernel")
-                g_ach = gst["grid_alg_bytes"] / (float(np.mean(g_ms)) * 1e-3) / 1e9
-                # DRAM bytes per non-zero and pass measured by ncu --set full on these kernels (profiles/r01_grid_dual_ncu_summary.txt:
-                # dram__bytes_read.sum + write = 4.59 GB for 9 passes over 48.0 M non-zeros = 10.6 B; r01_grid_tma_ncu_summary.txt:
-                # 10.3 B): u16 columns are streamed, so the kernels move LESS than the 12 B/nnz the roofline counts as algorithmic
-                passes = gst["em_iters_total"] + args.giant_loci
-                g_traffic = (10.63 if g_kernel == "em_grid_dual_kernel" else 10.34) * (gst["nnz"] / args.giant_loci) * passes
-                line["roofline_giant"] = {"bound": "hbm", "achieved": g_ach, "peak": peak, "unit": "GB/s", "frac": g_ach / peak,
-                                          "traffic": g_traffic, "traffic_source": "scaled from the ncu --set full capture of the same kernel in profiles/ (bytes per non-zero and pass)",
-                                          "kernel": g_kernel, "kernel_ms": float(np.mean(g_ms)),
-                                          "alg_bytes_per_launch": gst["grid_alg_bytes"], "peak_source": peak_src,
-                                          "workload": f"configs[3] shape: {args.giant_loci} loci x {args.giant_rows} rows, n_i=1, k~1+Poisson(47), T~U{{500..800}} "
-                                                      f"({gst['nnz']} nnz, {gst['em_iters_total']} EM iterations in total); CSR {gst['nnz'] * 12 / 1e9:.2f} GB > L2",
-                                          "value": gst["frag_iters"] / (float(np.mean(g_ms)) * 1e-3), "unit_value": UNIT}
-                qg.close()
-            except Exception as e:   # the headline line must still be printed
-                line["roofline_giant"] = {"error": repr(e)}
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline_sample(batch)
+            line["cpu_baseline"] = cpu_baseline_sample(job)
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# DRAM bytes per non-zero and EM pass of the giant-locus kernel, from `ncu --set full` captures of this kernel on this shape
+# (dram__bytes_read.sum + dram__bytes_write.sum of one launch / (passes x non-zeros)); see profiles/ for the capture files.
+GIANT_DRAM_BYTES_PER_NNZ_PASS = {"em_grid_dual_kernel": (10.63, "profiles/r01_grid_dual_ncu_summary.txt"),
+                                 "em_grid_tma_kernel": (10.34, "profiles/r01_grid_tma_ncu_summary.txt")}
+
+
+def giant_leg(args, api, partition, synth, local_rank, rank, world, flush, reduce_max, reduce_sum, barrier, dist, peak, peak_src):
+    """BASELINE configs[3]: `giant_loci` loci of `giant_rows` single-fragment rows, k ~ 1 + Poisson(47) isoforms per row,
+    T ~ U{500..800}, generated ON THE DEVICE from seed 4 (sbq_synth_giant: a locus is a pure function of (seed, global id), so
+    the partition does not change the data). Loci are dealt to the ranks by LPT (equal expected cost: round robin) and solved
+    in waves of `giant_wave` resident loci. One pass over all loci = one step; EM time from CUDA events inside libsbq."""
+    import torch
+    n, rows, seed = args.giant_loci, args.giant_rows, 4
+    owner = partition.lpt_partition(np.full(n, rows * 48, np.int64), world)
+    my_ids = [int(x) for x in owner[rank]]
+    qg = api.Quantifier(device=local_rank)
+    waves = [my_ids[i:i + args.giant_wave] for i in range(0, len(my_ids), args.giant_wave)]
+    # warm-up: a small wave through the same kernels (module load, first allocations)
+    qg.synth_giant(my_ids[:1] or [0], min(rows, 100_000), seed=seed)
+    qg.solve(rows)
+    barrier()
+    em_ms = solve_ms = gen_ms = 0.0
+    frag_iters = alg = iters = nnz = launches = 0
+    fpkm_local = 0.0
+    kernel = "em_grid_kernel"
+    t0 = time.perf_counter()
+    for ids in waves:
+        qg.clear()
+        qg.synth_giant(ids, rows, seed=seed)
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        qg.solve(rows * n)                       # total_mapped_reads of the whole 200-locus job
+        fpkm_local += qg.fpkm_sum()
+        qg.finalize_tpm(1.0)                     # placeholder denominator: TPM of a wave needs the all-reduced sum of ALL waves
+        qg.download()
+        st = qg.stats()
+        em_ms += st["grid_em_ms"]
+        solve_ms += st["solve_ms"]
+        gen_ms += st["upload_ms"]
+        frag_iters += st["frag_iters"]
+        alg += st["grid_alg_bytes"]
+        iters += st["em_iters_total"]
+        nnz += st["nnz"]
+        launches += st["kernel_launches"]
+        kernel = next((r["kernel"] for r in qg.launch_stats() if r["kernel"].startswith("em_grid")), kernel)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    barrier()
+    # the exchange step of this leg: the TPM denominator over all ranks and waves
+    g = torch.tensor([fpkm_local], dtype=torch.float64, device=torch.device("cuda", local_rank))
+    if world > 1:
+        dist.all_reduce(g)
+    qg.close()
+    em_max, solve_max, wall_max, gen_max = reduce_max(em_ms, solve_ms, wall, gen_ms)
+    fi, alg_all, it_all, nnz_all, launch_all = reduce_sum(frag_iters, alg, iters, nnz, launches)
+    ach = alg / (em_ms * 1e-3) / 1e9 if em_ms > 0 else 0.0          # this rank's kernel: algorithmic bytes / its own EM time
+    bpn, src = GIANT_DRAM_BYTES_PER_NNZ_PASS.get(kernel, (None, None))
+    passes = iters + len(my_ids)                                     # EM passes + one setup pass per locus
+    traffic = bpn * (nnz / max(len(my_ids), 1)) * passes if bpn else None
+    return {"scaling": "strong", "n_gpus": world,
+            "workload": f"configs[3]: {n} loci x {rows} single-fragment rows, k~1+Poisson(47) isoforms per row, T~U{{500..800}}, seed {seed}, generated on the device "
+                        f"({synth.DEVICE_GENERATOR_VERSION}); {int(nnz_all)} non-zeros = {nnz_all * 12 / 1e9:.1f} GB of CSR in total; LPT over {world} GPU(s), waves of <= {args.giant_wave} loci",
+            "value": fi / (solve_max * 1e-3), "unit": UNIT, "ms_per_step": solve_max, "em_ms_per_step": em_max, "generate_ms": gen_max,
+            "wall_ms_incl_generation": wall_max * 1e3, "em_iters_total": int(it_all), "loci_per_rank": len(my_ids), "gpu_launches": int(launch_all),
+            "fpkm_sum_allreduced": float(g.item()),
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                         "traffic_source": f"{bpn} DRAM bytes per non-zero and pass (ncu --set full of this kernel on this shape, {src}) x this rank's non-zeros per locus x passes"
+                                           if bpn else None,
+                         "real_bytes_frac": (bpn / 12.0) * ach / peak if bpn else None,
+                         "kernel": kernel, "kernel_ms": em_ms, "alg_bytes_per_launch": alg, "peak_source": peak_src, "rank": rank,
+                         "note": "kernel_ms sums the giant-locus launches of this rank's waves (each includes its one-off layout pass); "
+                                 "achieved counts the SURVEY 8d algorithmic bytes (12 B per non-zero); real_bytes_frac rescales to the DRAM bytes ncu measured "
+                                 "(u16 slots instead of 4-byte columns)"}}
 
 
 if __name__ == "__main__":

@@ -146,7 +146,7 @@ struct sbq_ctx {
 
    // deferred (GPU) weights
    int deferred = 0;                 // 0 = nothing queued yet, 1 = every queued locus is deferred, 2 = host-weighted batch
-   PinnedVec<int64_t> h_wseg;
+   PinnedVec<int64_t> h_wseg, h_wpool_off;   // h_wpool_off[l]: first pool element of deferred locus l (multi-GPU gather)
    PinnedVec<uint8_t> h_wn;
    PinnedVec<uint32_t> h_wmask, h_wpool;
    PinnedVec<int32_t> h_wlen;
@@ -254,7 +254,7 @@ void reset_batch(sbq_ctx* c) {
    c->have_cov = false;
    c->h_cov.clear();
    c->deferred = 0;
-   c->h_wseg.clear(); c->h_wn.clear(); c->h_wmask.clear(); c->h_wpool.clear(); c->h_wlen.clear();
+   c->h_wseg.clear(); c->h_wn.clear(); c->h_wmask.clear(); c->h_wpool.clear(); c->h_wlen.clear(); c->h_wpool_off.clear();
    c->resident = c->solved = c->downloaded = false;
 }
 
@@ -488,15 +488,15 @@ int launch_cluster_class_nt(sbq_ctx* c, const LaunchClass& lc, cudaStream_t st) 
 
 // Snapshot of the staging sizes, restored when a submit fails half-way (a failed call leaves the queue unchanged).
 struct StagingMark {
-   size_t lro, lio, rp, col, al, cnt, il, wseg, wn, wmask, wlen, wpool;
+   size_t lro, lio, rp, col, al, cnt, il, wseg, wn, wmask, wlen, wpool, wpoff;
    int64_t n_loci, n_row, n_iso, nnz;
    explicit StagingMark(const sbq_ctx* c)
        : lro(c->h_loc_row_off.n), lio(c->h_loc_iso_off.n), rp(c->h_row_ptr.n), col(c->h_col.n), al(c->h_alpha.n), cnt(c->h_count.n), il(c->h_iso_len.n),
-         wseg(c->h_wseg.n), wn(c->h_wn.n), wmask(c->h_wmask.n), wlen(c->h_wlen.n), wpool(c->h_wpool.n),
+         wseg(c->h_wseg.n), wn(c->h_wn.n), wmask(c->h_wmask.n), wlen(c->h_wlen.n), wpool(c->h_wpool.n), wpoff(c->h_wpool_off.n),
          n_loci(c->n_loci), n_row(c->n_row), n_iso(c->n_iso), nnz(c->nnz) {}
    void restore(sbq_ctx* c) const {
       c->h_loc_row_off.n = lro; c->h_loc_iso_off.n = lio; c->h_row_ptr.n = rp; c->h_col.n = col; c->h_alpha.n = al; c->h_count.n = cnt; c->h_iso_len.n = il;
-      c->h_wseg.n = wseg; c->h_wn.n = wn; c->h_wmask.n = wmask; c->h_wlen.n = wlen; c->h_wpool.n = wpool;
+      c->h_wseg.n = wseg; c->h_wn.n = wn; c->h_wmask.n = wmask; c->h_wlen.n = wlen; c->h_wpool.n = wpool; c->h_wpool_off.n = wpoff;
       c->n_loci = n_loci; c->n_row = n_row; c->n_iso = n_iso; c->nnz = nnz;
    }
 };
@@ -643,7 +643,7 @@ void sbq_destroy(sbq_ctx* c) {
    c->r_locus_fpkm.release(); c->r_keep.release(); c->r_iters.release(); c->r_status.release();
    c->d_in.release(); c->d_out.release(); c->d_lists.release(); c->d_grid_scratch.release(); c->d_col16.release(); c->d_rowrec.release(); c->d_csc.release(); c->d_synth.release(); c->d_bias.release();
    c->h_cov.release(); c->r_beta.release(); c->r_outer.release();
-   c->h_wseg.release(); c->h_wn.release(); c->h_wmask.release(); c->h_wpool.release(); c->h_wlen.release(); c->d_weights.release();
+   c->h_wseg.release(); c->h_wn.release(); c->h_wmask.release(); c->h_wpool.release(); c->h_wlen.release(); c->h_wpool_off.release(); c->d_weights.release();
    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
    for (auto& e : c->ev_join) if (e) cudaEventDestroy(e);
@@ -1213,7 +1213,7 @@ int sbq_submit_deferred(sbq_ctx* c, const sbq_table* const* tables, int64_t n_ta
       const StagingMark mark(c);
       const int64_t pool_base = (int64_t)c->h_wpool.n;
       const bool ok = c->h_wseg.reserve(c->h_wseg.n + nnz) && c->h_wn.append(d.n_seg, nnz) && c->h_wmask.append(d.implicit_mask, nnz) &&
-                      c->h_wlen.append(d.iso_len, nnz) && c->h_wpool.append(d.pool, d.n_pool);
+                      c->h_wlen.append(d.iso_len, nnz) && c->h_wpool.append(d.pool, d.n_pool) && c->h_wpool_off.append(&pool_base, 1);
       if (!ok) {
          mark.restore(c);
          return fail(c, SBQ_ERR_NOMEM, "pinned staging");

@@ -165,6 +165,25 @@ int multi_gather(sbq_ctx* par, sbq_ctx* ch, const std::vector<int32_t>& list) {
    }
    if (par->have_cov) { ch->n_cov = par->n_cov; ch->have_cov = true; }
    ch->deferred = 2;
+   if (par->deferred == 1) {
+      // deferred (GPU) weights: the per-entry descriptors travel with their loci, segment pointers re-based into the child's pool
+      if (!ch->h_wseg.reserve(nnz) || !ch->h_wn.reserve(nnz) || !ch->h_wmask.reserve(nnz) || !ch->h_wlen.reserve(nnz)) return fail(ch, SBQ_ERR_NOMEM, "pinned staging");
+      for (int32_t l : list) {
+         const int64_t k0 = rp[lro[l]], k1 = rp[lro[l + 1]];
+         const int64_t p0 = par->h_wpool_off.p[l], p1 = (size_t)l + 1 < par->h_wpool_off.n ? par->h_wpool_off.p[l + 1] : (int64_t)par->h_wpool.n;
+         const int64_t shift = (int64_t)ch->h_wpool.n - p0;
+         if (!ch->h_wpool.append(par->h_wpool.p + p0, (size_t)(p1 - p0))) return fail(ch, SBQ_ERR_NOMEM, "pinned staging");
+         for (int64_t k = k0; k < k1; ++k) ch->h_wseg.p[ch->h_wseg.n++] = par->h_wseg.p[k] < 0 ? -1 : par->h_wseg.p[k] + shift;
+         ch->h_wn.append(par->h_wn.p + k0, (size_t)(k1 - k0));
+         ch->h_wmask.append(par->h_wmask.p + k0, (size_t)(k1 - k0));
+         ch->h_wlen.append(par->h_wlen.p + k0, (size_t)(k1 - k0));
+      }
+      ch->model = par->model;
+      ch->model_emp = par->model_emp;
+      ch->model_read_len = par->model_read_len;
+      ch->have_model = par->have_model;
+      ch->deferred = 1;
+   }
    return SBQ_SUCCESS;
 }
 
@@ -173,7 +192,7 @@ int multi_upload(sbq_ctx* c) {
    std::lock_guard<std::mutex> lk(c->mu);
    if (c->n_loci == 0) return fail(c, SBQ_ERR_STATE, "nothing submitted");
    if (c->host_released) return fail(c, SBQ_ERR_STATE, "the borrowed batch was released by the previous sbq_upload: sbq_clear and submit again");
-   if (c->deferred == 1) return fail(c, SBQ_ERR_UNSUPPORTED, "deferred-weight batches are single-device (n_gpus = 1)");
+   if (c->deferred == 1 && !c->have_model) return fail(c, SBQ_ERR_STATE, "deferred weights need sbq_set_insert_model()");
    if (c->cfg.bias_mode == 1 && !c->have_cov) return fail(c, SBQ_ERR_STATE, "bias_mode = 1 needs sbq_set_covariates() after the last submit");
    const int n = (int)m.child.size();
    const int64_t *lro = loc_row_off(c), *lio = loc_iso_off(c), *rp = row_ptr(c);

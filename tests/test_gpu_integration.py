@@ -15,6 +15,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REFDIR = os.path.join(ROOT, "oracle", "_ref")
 BINS = [os.path.join(REFDIR, b) for b in ("strawberry_ref", "strawberry_sbq", "samtools_ref")]
+BATCHED = os.path.join(REFDIR, "strawberry_sbq_batched")
 
 
 def parse_gtf(path):
@@ -97,3 +98,76 @@ def test_fragment_context_tsv_matches_reference(tmp_path):
                     assert abs(fu - fv) <= 1e-9 * max(abs(fu), 1e-30) + (2e-6 if k != hdr.index("conditional_probabilities") else 0.0), (hdr[k], u, v)
             else:
                 assert x == y, (hdr[k], x, y)
+
+
+def gtf_body(path):
+    """GTF records; the leading comment lines carry the command line (binary name, output paths) and are skipped"""
+    return [l for l in open(path, "rb").read().split(b"\n") if l and not l.startswith(b"#")]
+
+
+def theta_lines(path):
+    return sorted(l for l in open(path, "rb").read().split(b"\n") if b"raw read count" in l)
+
+
+def make_bam(tmp_path, n_genes, seed, parallel=False):
+    sam, gtf, bam = (str(tmp_path / n) for n in ("s.sam", "s.gtf", "s.bam"))
+    info = (samgen.write_dataset_parallel if parallel else samgen.write_dataset)(sam, gtf, n_genes=n_genes, seed=seed)
+    with open(bam, "wb") as fh:
+        subprocess.run([BINS[2], "view", "-bS", sam], check=True, stdout=fh, stderr=subprocess.DEVNULL)
+    os.remove(sam)
+    return bam, gtf, info
+
+
+def test_batched_dropin_is_byte_exact(tmp_path):
+    """SURVEY 8f.4 / INTEGRATION.md section 3: the BATCHED drop-in (one sbq_run for the whole sample, class weights on the
+    GPU) against the unmodified reference binary as a byte-for-byte diff: the GTF records in order with -p 1, the sorted
+    records with -p 4, and the theta log lines (%f, src/estimate.cpp:311-313) as a sorted multiset."""
+    if not all(os.path.exists(b) for b in BINS + [BATCHED]):
+        pytest.skip("oracle/_ref binaries not built (make -C integration)")
+    bam, gtf, info = make_bam(tmp_path, 150, 3)
+    out, log = str(tmp_path / "ref.gtf"), str(tmp_path / "ref.log")
+    run(BINS[0], bam, gtf, out, log, 1)
+    ref_gtf, ref_theta = gtf_body(out), theta_lines(log)
+    assert len(ref_gtf) > info["n_isoforms"] and len(ref_theta) > 100
+    for threads in (1, 4):
+        out, log = str(tmp_path / f"b{threads}.gtf"), str(tmp_path / f"b{threads}.log")
+        run(BATCHED, bam, gtf, out, log, threads)
+        got = gtf_body(out)
+        if threads == 1:
+            assert got == ref_gtf, "GTF records differ from the reference (byte diff, -p 1, in order)"
+        assert sorted(got) == sorted(ref_gtf), f"sorted GTF records differ from the reference (-p {threads})"
+        assert theta_lines(log) == ref_theta, f"theta log lines differ from the reference (-p {threads})"
+
+
+def test_batched_dropin_one_million_fragments(tmp_path):
+    """The real program on a >= 1 M-fragment synthetic BAM (2992 genes, ~10 k isoforms): reference binary (-p 1) vs the
+    batched drop-in with -p 1 and -p nproc - sorted GTF records and sorted theta log lines byte-identical - and the wall /
+    quantification-only times of both (also written to gpurun_out/ when that directory exists)."""
+    import json
+    import time
+    if not all(os.path.exists(b) for b in BINS + [BATCHED]):
+        pytest.skip("oracle/_ref binaries not built (make -C integration)")
+    bam, gtf, info = make_bam(tmp_path, 3000, 5, parallel=True)
+    assert info["n_fragments"] >= 1_000_000
+    timed = os.path.join(REFDIR, "strawberry_ref_timed")
+    rows = []
+
+    def timed_run(tag, binary, threads, **env):
+        out, log = str(tmp_path / f"{tag}.gtf"), str(tmp_path / f"{tag}.log")
+        cmd = [binary, bam, "-g", gtf, "-r", "-o", out, "-T", log, "-p", str(threads)]
+        t0 = time.perf_counter()
+        r = subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, timeout=900, env=dict(os.environ, SBQ_TIMING="1", **env))
+        wall = time.perf_counter() - t0
+        rows.append(dict(run=tag, threads=threads, wall_s=round(wall, 3), timing=[l for l in r.stderr.splitlines() if l.startswith("SBQ_TIMING")]))
+        return sorted(gtf_body(out)), theta_lines(log)
+
+    ref = timed_run("reference", timed if os.path.exists(timed) else BINS[0], 1)
+    nproc = os.cpu_count() or 4
+    for tag, threads in (("batched_p1", 1), (f"batched_p{nproc}", nproc)):
+        got = timed_run(tag, BATCHED, threads)
+        assert len(got[0]) == len(ref[0]) and got[0] == ref[0], f"{tag}: sorted GTF records differ from the reference"
+        assert got[1] == ref[1], f"{tag}: theta log lines differ from the reference"
+    print(json.dumps(dict(dataset=info, runs=rows), indent=1))
+    outdir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(outdir):
+        json.dump(dict(dataset=info, runs=rows), open(os.path.join(outdir, "integration_1m_timing.json"), "w"), indent=1)

@@ -95,3 +95,30 @@ def test_c_abi_n_gpus_beyond_the_box_is_refused():
     with pytest.raises(api.SbqError) as e:
         api.Quantifier(device=0, n_gpus=torch.cuda.device_count() + 1)
     assert e.value.code == api.SBQ_ERR_NO_DEVICE
+
+
+def test_integrated_binary_on_n_gpus_gives_the_same_gtf(tmp_path):
+    """The batched drop-in binary with SBQ_N_GPUS = all devices of the box (loci LPT-partitioned inside libsbq, one
+    ncclAllReduce for the TPM denominator) writes the same GTF records as on one GPU."""
+    import subprocess
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import samgen
+    refdir = os.path.join(ROOT, "oracle", "_ref")
+    binary, samtools = os.path.join(refdir, "strawberry_sbq_batched"), os.path.join(refdir, "samtools_ref")
+    if not (os.path.exists(binary) and os.path.exists(samtools)):
+        pytest.skip("oracle/_ref binaries not built (make -C integration)")
+    sam, gtf, bam = (str(tmp_path / x) for x in ("s.sam", "s.gtf", "s.bam"))
+    samgen.write_dataset(sam, gtf, n_genes=200, seed=12)
+    with open(bam, "wb") as fh:
+        subprocess.run([samtools, "view", "-bS", sam], check=True, stdout=fh, stderr=subprocess.DEVNULL)
+    outs = []
+    for tag, env in (("one", {}), ("many", {"SBQ_N_GPUS": str(n)})):
+        out = str(tmp_path / f"{tag}.gtf")
+        subprocess.run([binary, bam, "-g", gtf, "-r", "-o", out, "-T", str(tmp_path / f"{tag}.log"), "-p", "2"], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600, env=dict(os.environ, **env))
+        outs.append(sorted(l for l in open(out, "rb").read().split(b"\n") if l and not l.startswith(b"#")))
+    assert len(outs[0]) > 500 and outs[0] == outs[1]
