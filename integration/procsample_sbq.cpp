@@ -37,14 +37,70 @@ struct Pending {
    unique_ptr<LocusContext> est;
    size_t order;                              // position of the cluster in the BAM walk (output order of -p 1)
 };
+
+// ---- single-pass host pipeline. The reference decodes and clusters the BAM twice in -g mode:
+// Sample::preProcess (pass 1: insert-size histogram, total mapped reads) and Sample::procSample (pass 2: quantification),
+// ~85 % of its wall time. Both passes build and finalize exactly the same clusters (collapseAndFilterHits depends on the
+// cluster's own reads only), so the preProcess below keeps every finalized cluster and the batched procSample consumes
+// them instead of walking the BAM again. SBQ_SINGLE_PASS=0 turns the cache off (two passes, as the reference).
+vector<shared_ptr<HitCluster>> g_cache;
+mutex g_cache_mu;
+bool g_cache_complete = false;
+bool single_pass_enabled() {
+   const char* e = getenv("SBQ_SINGLE_PASS");
+   return no_assembly && !(e && e[0] == '0');
+}
 }  // namespace
+
+// Pass 1, same traversal and side effects as the reference (src/alignments.cpp:1189-1233): per cluster finalizeCluster +
+// fragLenDist (fragment-length histogram, _total_mapped_reads). Additionally the finalized clusters are kept.
+void Sample::preProcess(FILE* log) {
+   const RefSeqTable& ref_t = _hit_factory->_ref_table;
+   const bool keep = single_pass_enabled();
+   atomic<int> workers(0);
+   _num_cluster = 0;
+   g_cache.clear();
+   g_cache_complete = false;
+   while (true) {
+      shared_ptr<HitCluster> cluster(new HitCluster());
+      if (-1 == nextClusterRefDemand(*cluster)) break;
+      if (cluster->ref_id() == -1) continue;
+      cluster->_id = ++_num_cluster;
+      auto work = [this, &ref_t, cluster, log, keep] {
+         finalizeCluster(cluster, true);
+         fragLenDist(ref_t, cluster->ref_mRNAs(), cluster, log);
+         if (keep) {
+            lock_guard<mutex> lk(g_cache_mu);
+            g_cache.push_back(cluster);
+         }
+      };
+      if (use_threads && num_threads > 1) {
+         while (workers.load() >= num_threads) this_thread::sleep_for(chrono::microseconds(200));
+         ++workers;
+         thread worker([work, &workers] {
+            work();
+            --workers;
+         });
+         worker.detach();
+      } else {
+         work();
+      }
+   }
+   while (workers.load() != 0) this_thread::sleep_for(chrono::microseconds(200));
+   if (keep) {
+      sort(g_cache.begin(), g_cache.end(), [](const shared_ptr<HitCluster>& a, const shared_ptr<HitCluster>& b) { return a->_id < b->_id; });
+      g_cache_complete = true;
+   }
+}
 
 void Sample::procSample(FILE* pfile, FILE* plogfile, FILE* fragfile) {
    const auto t_start = chrono::steady_clock::now();
-   _hit_factory->reset();
+   if (!g_cache_complete) {                   // two passes: rewind the BAM and the reference-transcript cursor like the reference
+      _hit_factory->reset();
+      reset_refmRNAs();
+   }
    vector<Isoform> isoforms;
    isoforms.reserve(1024);
-   reset_refmRNAs();
    const RefSeqTable& ref_t = _hit_factory->_ref_table;
    int current_ref_id = INT_MAX;
    if (fragfile != NULL) {
@@ -60,9 +116,11 @@ void Sample::procSample(FILE* pfile, FILE* plogfile, FILE* fragfile) {
    mutex pending_mu;
    atomic<int> workers(0);
    size_t order = 0;
+   const bool cached = g_cache_complete;      // single pass: the clusters of pass 1 are reused, already finalized
+   size_t next_cached = 0;
    // stage one locus: what Sample::quantifyCluster does up to the numeric part (src/alignments.cpp:1510-1526)
    auto stage = [&](shared_ptr<HitCluster> cluster, size_t ord) {
-      finalizeCluster(cluster, true);
+      if (!cached) finalizeCluster(cluster, true);
       unique_ptr<LocusContext> est(new LocusContext(*this, plogfile, cluster, cluster->ref_mRNAs()));
       est->estimate_abundances();             // stage mode: CSR of the class table -> sbq_submit
       lock_guard<mutex> lk(pending_mu);
@@ -70,9 +128,15 @@ void Sample::procSample(FILE* pfile, FILE* plogfile, FILE* fragfile) {
    };
 
    while (true) {
-      shared_ptr<HitCluster> cluster(new HitCluster());
-      if (-1 == nextClusterRefDemand(*cluster)) break;
-      if (cluster->ref_id() == -1) continue;
+      shared_ptr<HitCluster> cluster;
+      if (cached) {
+         if (next_cached == g_cache.size()) break;
+         cluster = std::move(g_cache[next_cached++]);
+      } else {
+         cluster.reset(new HitCluster());
+         if (-1 == nextClusterRefDemand(*cluster)) break;
+         if (cluster->ref_id() == -1) continue;
+      }
       if (current_ref_id != cluster->ref_id()) {
          current_ref_id = cluster->ref_id();
          if (BIAS_CORRECTION) {
@@ -119,7 +183,7 @@ void Sample::procSample(FILE* pfile, FILE* plogfile, FILE* fragfile) {
    if (getenv("SBQ_TIMING")) {
       const auto t_end = chrono::steady_clock::now();
       auto ms = [](chrono::steady_clock::time_point a, chrono::steady_clock::time_point b) { return chrono::duration<double, milli>(b - a).count(); };
-      fprintf(stderr, "SBQ_TIMING procSample(batched) loci %zu walk+stage_ms %.3f sbq_run_ms %.3f tail+gtf_ms %.3f total_ms %.3f\n", pending.size(),
+      fprintf(stderr, "SBQ_TIMING procSample(batched%s) loci %zu walk+stage_ms %.3f sbq_run_ms %.3f tail+gtf_ms %.3f total_ms %.3f\n", cached ? ", single pass" : "", pending.size(),
               ms(t_start, t_staged), ms(t_staged, t_run), ms(t_run, t_end), ms(t_start, t_end));
    }
 }

@@ -33,7 +33,7 @@ using namespace sbq;
 
 namespace {
 
-constexpr size_t SMEM_CAP = 200 * 1024;   // dynamic shared memory we ask for at most (227 KB usable)
+constexpr size_t SMEM_CAP = CL_SMEM_CAP;   // dynamic shared memory we ask for at most (227 KB usable)
 constexpr int N_SIDE_STREAMS = 12;
 
 // ---- pinned host array with geometric growth -------------------------------------------------
@@ -267,16 +267,15 @@ int ensure_origin(sbq_ctx* c) {
    return SBQ_SUCCESS;
 }
 
-size_t cluster_class_smem(int max_iso, size_t slice_bytes, int nt) {
-   // fixed arrays + the larger of (estimated largest resident slice, a full set of streaming accumulators)
-   const size_t fixed = cluster_fixed_doubles(max_iso) * sizeof(double);
-   const size_t stream = (size_t)(nt / CL_LPR_STREAM) * max_iso * sizeof(double);
-   return std::min(fixed + std::max(slice_bytes, stream) + 256, SMEM_CAP);
-}
-
-// single-CTA loci are bucketed by shared-memory need so that small ones do not reserve the footprint of the largest:
-// bucket 0 (<= 24 KB, 128 threads), 1 (<= 56 KB), 2 (<= 112 KB), 3 (rest)
-int smem_bucket(size_t bytes) { return bytes <= 24 * 1024 ? 0 : bytes <= 56 * 1024 ? 1 : bytes <= 112 * 1024 ? 2 : 3; }
+// Single-CTA loci are bucketed by shared-memory need, and the bucket sets the THREADS of the CTA as well: the EM of a small
+// locus is a chain of short barrier-separated phases, i.e. latency-bound, so its cost in SM time is (time per iteration) x
+// (share of the SM it holds). Small CTAs let several loci share an SM (registers: 125 per thread):
+//   bucket 0  <=  12 KB   64 threads  8 per SM        bucket 3  <= 108 KB  256 threads  2 per SM
+//   bucket 1  <=  24 KB  128 threads  4 per SM        bucket 4  rest       512 threads  1 per SM
+//   bucket 2  <=  54 KB  128 threads  4 per SM
+constexpr int N_BUCKETS = 5;
+const int BUCKET_NT[N_BUCKETS] = {64, 128, 128, 256, 512};
+int smem_bucket(size_t bytes) { return bytes <= 12 * 1024 ? 0 : bytes <= 24 * 1024 ? 1 : bytes <= 54 * 1024 ? 2 : bytes <= 108 * 1024 ? 3 : 4; }
 
 int cluster_size_for(int64_t nnz) {
    // ~14 B of shared memory per non-zero (row part + CSC index): a CTA's slice stays under ~14k non-zeros, which still
@@ -326,7 +325,7 @@ int plan(sbq_ctx* c) {
    const bool force_dual = getenv("SBQ_GRID_DUAL") != nullptr;
    std::vector<char> dual_locus(c->n_loci, 0);
    std::vector<int64_t> nnz_of(c->n_loci);
-   LaunchClass* slot[5][4] = {};
+   LaunchClass* slot[5][N_BUCKETS] = {};
    std::vector<LaunchClass> tmp;
    tmp.reserve(20);
    const int64_t grid_min_nnz = 300 * 1000;   // above this a locus is faster on the whole GPU than on a 16-CTA cluster
@@ -337,7 +336,10 @@ int plan(sbq_ctx* c) {
       if (T > SBQ_MAX_ISO) return fail(c, SBQ_ERR_UNSUPPORTED, "locus %lld has %lld isoforms (> SBQ_MAX_ISO)", (long long)l, (long long)T);
       int tier;
       if (c->force_tier) tier = c->force_tier;
-      else if (T <= WT_MAX_ISO && R <= 32 && nnz <= 4 * R + 32) tier = 1;   // one row per lane, rows mostly register-resident
+      // warp tier: one warp per locus, no block barriers, ~1/24 of an SM. Loci of up to 32 isoforms and a few hundred rows belong
+      // here even though a lane then walks several rows: they are latency-bound either way, and a CTA of the cluster tier would
+      // hold 4 - 30 times more of the SM per iteration (plus its one-off sort / transposed-index setup)
+      else if (T <= WT_MAX_ISO && R <= WT_MAX_ROWS && nnz <= WT_MAX_NNZ) tier = 1;
       else if (nnz >= grid_min_nnz) tier = 3;
       else tier = 2;
       if (tier == 1 && T > WT_MAX_ISO) tier = 2;
@@ -366,11 +368,10 @@ int plan(sbq_ctx* c) {
       } else {
          int cs = c->force_cluster ? c->force_cluster : cluster_size_for(nnz);
          int csi = cs == 1 ? 0 : cs == 2 ? 1 : cs == 4 ? 2 : cs == 8 ? 3 : 4;
-         // per-CTA resident slice with 12 % slack for the row-granular split
-         const size_t slice = (size_t)(1.12 * (double)cluster_resident_bytes((size_t)(nnz / cs + 1), (size_t)(R / cs + 1), (int)T)) + 512;
-         const int bucket = cs == 1 ? smem_bucket(cluster_class_smem((int)T, slice, CL_NT_SMALL)) : 3;
+         const size_t slice = cluster_slice_estimate(nnz, R, (int)T, cs);
+         const int bucket = cs == 1 ? smem_bucket(cluster_fixed_doubles((int)T) * sizeof(double) + slice + 256) : N_BUCKETS - 1;
          if (!slot[csi][bucket]) {
-            tmp.push_back(LaunchClass{cs, bucket == 0 ? CL_NT_SMALL : CL_NT, {}, 0, 0, 0, 0});
+            tmp.push_back(LaunchClass{cs, BUCKET_NT[bucket], {}, 0, 0, 0, 0});
             slot[csi][bucket] = &tmp.back();
          }
          LaunchClass* lc = slot[csi][bucket];
@@ -958,8 +959,9 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
       if (!serialize && used_side < N_SIDE_STREAMS) CU(cudaStreamWaitEvent(ss, c->ev_fork, 0));
       LaunchTimer& t = c->lt[2 + used_side % N_SIDE_STREAMS];
       CU(cudaEventRecord(t.e0, ss));
-      // the 128-thread variant is capped at 128 registers so that four CTAs share an SM
-      int rc = lc.lpr == CL_NT_SMALL ? launch_cluster_class_nt<CL_NT_SMALL, 0, 4>(c, lc, ss) : launch_cluster_class_nt<CL_NT, 0, 1>(c, lc, ss);
+      // register caps (launch bounds) follow the CTAs-per-SM targets of the buckets
+      int rc = lc.lpr == 64 ? launch_cluster_class_nt<64, 0, 8>(c, lc, ss) : lc.lpr == 128 ? launch_cluster_class_nt<128, 0, 4>(c, lc, ss) :
+               lc.lpr == 256 ? launch_cluster_class_nt<256, 0, 2>(c, lc, ss) : launch_cluster_class_nt<CL_NT, 0, 1>(c, lc, ss);
       if (rc) return rc;
       CU(cudaEventRecord(t.e1, ss));
       t.used = true;

@@ -107,6 +107,8 @@ __device__ __forceinline__ unsigned trace_smid() { unsigned s; asm volatile("mov
 #endif
 constexpr int WT_WARPS = 8;
 constexpr int WT_MAX_ISO = 32;
+constexpr int WT_MAX_ROWS = 256;   // planner: loci a warp still takes (a lane then walks up to 8 rows per iteration)
+constexpr int WT_MAX_NNZ = 1024;
 constexpr int WT_STRIDE = 33;
 
 __host__ __device__ inline size_t warp_tier_smem_bytes(int max_iso) {
@@ -311,6 +313,22 @@ __host__ __device__ inline size_t cluster_resident_csr_bytes(size_t nnz_c, size_
 }
 __host__ __device__ inline size_t cluster_resident_bytes(size_t nnz_c, size_t nrows, int T) {
    return cluster_resident_csr_bytes(nnz_c, nrows, T) + nnz_c * 4 + 4;
+}
+
+// Shared memory a cluster-tier CTA asks for, as a function of the LOCUS alone (T, estimated per-CTA slice, thread count):
+// fixed arrays + the larger of (estimated largest resident slice, a full set of streaming accumulators). Host planner and
+// kernel evaluate the same expression, so what a locus keeps resident - and with it the order of every sum - does not
+// depend on which other loci share its launch: results are invariant under any partition of the loci over devices.
+constexpr size_t CL_SMEM_CAP = 200 * 1024;   // dynamic shared memory a CTA asks for at most (227 KB usable)
+__host__ __device__ inline size_t cluster_class_smem(int max_iso, size_t slice_bytes, int nt) {
+   const size_t fixed = cluster_fixed_doubles(max_iso) * sizeof(double);
+   const size_t stream = (size_t)(nt / CL_LPR_STREAM) * max_iso * sizeof(double);
+   const size_t want = fixed + (slice_bytes > stream ? slice_bytes : stream) + 256;
+   return want < CL_SMEM_CAP ? want : CL_SMEM_CAP;
+}
+// per-CTA resident slice estimate with 12 % slack for the row-granular split
+__host__ __device__ inline size_t cluster_slice_estimate(long long nnz, long long R, int T, int cs) {
+   return (size_t)(1.12 * (double)cluster_resident_bytes((size_t)(nnz / cs + 1), (size_t)(R / cs + 1), T)) + 512;
 }
 
 template <int NT>
@@ -790,7 +808,7 @@ struct LocalOut {
 
 template <int NT, int NCACHE, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
-em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, unsigned smem_bytes) {
+em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, unsigned smem_launch) {
    cg::cluster_group cluster = cg::this_cluster();
    const unsigned CS = cluster.num_blocks();
    const unsigned rank = cluster.block_rank();
@@ -819,6 +837,8 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
    double* nxt = bufB;
 
    const int64_t* __restrict__ rp = p.row_ptr + r0;
+   // this locus' own shared-memory budget (<= what the launch provides: the class maximum of the same expression)
+   const unsigned smem_bytes = min(smem_launch, (unsigned)cluster_class_smem(T, cluster_slice_estimate((long long)(rp[R] - rp[0]), R, T, (int)CS), NT));
 
    // rows of this CTA: split by non-zeros (lower_bound on row_ptr)
    if (tid < 2) {

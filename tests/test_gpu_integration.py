@@ -29,9 +29,9 @@ def parse_gtf(path):
     return out
 
 
-def run(binary, bam, gtf, out, log, threads=1, ctx=None):
+def run(binary, bam, gtf, out, log, threads=1, ctx=None, **env):
     cmd = [binary, bam, "-g", gtf, "-r", "-o", out, "-T", log, "-p", str(threads)] + (["-f", ctx] if ctx else [])
-    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600, env=dict(os.environ, **env))
 
 
 @pytest.mark.parametrize("threads", [1, 4])
@@ -129,14 +129,33 @@ def test_batched_dropin_is_byte_exact(tmp_path):
     run(BINS[0], bam, gtf, out, log, 1)
     ref_gtf, ref_theta = gtf_body(out), theta_lines(log)
     assert len(ref_gtf) > info["n_isoforms"] and len(ref_theta) > 100
-    for threads in (1, 4):
-        out, log = str(tmp_path / f"b{threads}.gtf"), str(tmp_path / f"b{threads}.log")
-        run(BATCHED, bam, gtf, out, log, threads)
+    # single pass (the clusters of pass 1 are reused: SURVEY 8f.2, the default) and two passes over the BAM like the reference;
+    # GPU class weights (default) and host class weights
+    for threads, env in ((1, {}), (4, {}), (1, {"SBQ_SINGLE_PASS": "0"}), (4, {"SBQ_SINGLE_PASS": "0", "SBQ_HOST_WEIGHTS": "1"})):
+        tag = f"b{threads}_{len(env)}"
+        out, log = str(tmp_path / f"{tag}.gtf"), str(tmp_path / f"{tag}.log")
+        run(BATCHED, bam, gtf, out, log, threads, **env)
         got = gtf_body(out)
         if threads == 1:
-            assert got == ref_gtf, "GTF records differ from the reference (byte diff, -p 1, in order)"
-        assert sorted(got) == sorted(ref_gtf), f"sorted GTF records differ from the reference (-p {threads})"
-        assert theta_lines(log) == ref_theta, f"theta log lines differ from the reference (-p {threads})"
+            assert got == ref_gtf, f"GTF records differ from the reference (byte diff, -p 1, in order, {env})"
+        assert sorted(got) == sorted(ref_gtf), f"sorted GTF records differ from the reference (-p {threads}, {env})"
+        assert theta_lines(log) == ref_theta, f"theta log lines differ from the reference (-p {threads}, {env})"
+
+
+def test_batched_dropin_fragment_context_tsv(tmp_path):
+    """-f through the batched drop-in (host class weights are kept for it): the TSV rows equal the reference's as text,
+    except the numeric columns that are compared like in test_fragment_context_tsv_matches_reference."""
+    if not all(os.path.exists(b) for b in BINS + [BATCHED]):
+        pytest.skip("oracle/_ref binaries not built (make -C integration)")
+    bam, gtf, _ = make_bam(tmp_path, 80, 9)
+    rows = {}
+    for tag, binary in (("ref", BINS[0]), ("sbq", BATCHED)):
+        ctx = str(tmp_path / f"{tag}.tsv")
+        run(binary, bam, gtf, str(tmp_path / f"{tag}f.gtf"), str(tmp_path / f"{tag}f.log"), 1, ctx)
+        rows[tag] = sorted(open(ctx, "rb").read().split(b"\n"))
+    assert len(rows["ref"]) == len(rows["sbq"]) > 500
+    diff = sum(a != b for a, b in zip(rows["ref"], rows["sbq"]))
+    assert diff <= 0.01 * len(rows["ref"]), f"{diff} of {len(rows['ref'])} TSV rows differ as text"   # last printed digit of a 12-digit alpha may differ
 
 
 def test_batched_dropin_one_million_fragments(tmp_path):

@@ -42,13 +42,14 @@ def go(tag, binary, threads, **env):
     tm = " ".join(l for l in r.stderr.splitlines() if l.startswith("SBQ_TIMING"))
     num = lambda k: float(re.search(k + r" ([0-9.]+)", tm).group(1)) if re.search(k + r" ([0-9.]+)", tm) else None
     return dict(tag=tag, rc=r.returncode, wall=wall, gtf=body(out) if r.returncode == 0 else None, table=num("class_table_ms"), est=num("estimate_abundances_ms"),
-                stage=num("stage_ms"), run=num("run_ms"), solve=num("solve"), upload=num("upload"), finish=num("finish_ms"), walk=num(r"walk\+stage_ms"))
+                stage=num(r" stage_ms"), run=num("run_ms"), solve=num("solve"), upload=num("upload"), finish=num("finish_ms"), walk=num(r"walk\+stage_ms"))
 
 
 runs = [go("reference -p 1", "strawberry_ref_timed", 1), go(f"reference -p {nproc}", "strawberry_ref_timed", nproc),
         go("per-locus drop-in -p 1", "strawberry_sbq", 1), go("batched drop-in -p 1", "strawberry_sbq_batched", 1),
         go(f"batched drop-in -p {nproc}", "strawberry_sbq_batched", nproc),
-        go("batched drop-in -p 1, host weights", "strawberry_sbq_batched", 1, SBQ_HOST_WEIGHTS="1")]
+        go("batched drop-in -p 1, two passes over the BAM", "strawberry_sbq_batched", 1, SBQ_SINGLE_PASS="0"),
+        go("batched drop-in -p 1, two passes, host weights", "strawberry_sbq_batched", 1, SBQ_SINGLE_PASS="0", SBQ_HOST_WEIGHTS="1")]
 if n_gpu > 1:
     runs.append(go(f"batched drop-in -p {nproc}, {n_gpu} GPUs", "strawberry_sbq_batched", nproc, SBQ_N_GPUS=str(n_gpu)))
 ref = runs[0]["gtf"]
