@@ -33,6 +33,8 @@ import time
 
 import numpy as np
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before CUDA is initialised: one hardware queue per concurrent launch
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -254,7 +256,7 @@ def main():
             t0 = time.perf_counter()
             q.clear()
             q.submit_flat(pinned)        # page-locked arrays are used in place
-            q.upload()
+            q.upload_begin()             # copies enqueued in the order the solve needs them; launches wait for their own data only
             q.solve(total_reads)
             tpm_exchange(q)
             q.download()
@@ -314,7 +316,7 @@ def main():
                         "for up to 1000 sequential EM iterations, so this step is bound by per-iteration latency of its longest loci, not by HBM "
                         "(DRAM traffic of the phase is a few tens of MB: traffic is not meaningful here); the HBM-bound kernel of this path is the "
                         "giant-locus one, see `giant.roofline`",
-                "launches": [{k: r[k] for k in ("kernel", "cluster_size", "n_loci", "nnz", "ms", "alg_bytes", "max_iters")} for r in launches]}
+                "launches": [{k: r[k] for k in ("kernel", "cluster_size", "threads", "n_loci", "nnz", "start_ms", "ms", "alg_bytes", "max_iters")} for r in launches]}
 
     line = {"metric": METRIC, "value": total_frag_iters / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -148,6 +148,12 @@ void  sbq_host_free(void* p);
  *   sbq_solve     EM kernels + FPKM/frac/filter epilogue on the resident batch; re-runnable
  *   sbq_download  D2H of theta, fpkm, frac, keep, iters, status and the local FPKM sum        */
 int  sbq_upload(sbq_ctx*);
+/* Asynchronous sbq_upload: returns as soon as the copies are ENQUEUED - offsets and columns first, then the weights of the
+ * largest loci launch by launch, then the rest - and a following sbq_solve lets every kernel launch wait only for the copies
+ * it needs, so the longest-running loci iterate while the tail of the batch is still crossing PCIe. Borrowed (page-locked,
+ * in-place) arrays must stay valid until that sbq_solve returns. sbq_run uses it. Multi-GPU, deferred-weight and bias
+ * batches fall back to the synchronous sbq_upload. */
+int  sbq_upload_begin(sbq_ctx*);
 int  sbq_solve(sbq_ctx*, int64_t total_mapped_reads);
 int  sbq_download(sbq_ctx*);
 
@@ -177,13 +183,14 @@ int  sbq_get_stats(const sbq_ctx*, sbq_stats* out);
 typedef struct {
    int32_t kind;            /* 1 = warp tier, 2 = cluster tier, 3 = grid (giant-locus) tier               */
    int32_t cluster_size;    /* CTAs per locus (cluster tier)                                              */
-   int32_t lanes_per_row;
+   int32_t lanes_per_row;   /* threads per CTA of the launch (cluster tier)                               */
    int32_t variant;         /* grid tier: 1 = register-staged loads, 2 = TMA ring, 3 = bank-aligned two-slot layout */
    int64_t n_loci, nnz;
    double  ms;              /* kernel duration                                                            */
    int64_t alg_bytes;       /* sum over its loci of (12 nnz + 12 R + 16 T) * iters                         */
    int64_t frag_iters;
    int64_t max_iters;       /* longest EM run among its loci (the launch's critical path)                 */
+   double  start_ms;        /* when the launch's start event fired, relative to the start of sbq_solve    */
 } sbq_launch_stat;
 int  sbq_get_launch_stats(const sbq_ctx*, sbq_launch_stat* out, int cap);
 

@@ -12,6 +12,10 @@ import ctypes
 import os
 import weakref
 
+# a solve runs ~12 kernels concurrently, one stream each: more hardware work queues than the default 8 (no effect once the
+# process has created its CUDA context - import this module, or export the variable, before touching CUDA)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -24,7 +28,7 @@ LOCUS_OK, LOCUS_ITER_CAP, LOCUS_ZERO_DENOM, LOCUS_NO_ROWS = 0, 1, 2, 3
 ABI_SYMBOLS = [
     "sbq_abi_version", "sbq_error_string", "sbq_last_error", "sbq_config_default", "sbq_create", "sbq_destroy",
     "sbq_submit", "sbq_submit_flat", "sbq_clear", "sbq_validate", "sbq_host_alloc", "sbq_host_free",
-    "sbq_upload", "sbq_solve", "sbq_download", "sbq_run", "sbq_fpkm_sum", "sbq_fpkm_sum_to_device",
+    "sbq_upload", "sbq_upload_begin", "sbq_solve", "sbq_download", "sbq_run", "sbq_fpkm_sum", "sbq_fpkm_sum_to_device",
     "sbq_finalize_tpm", "sbq_results", "sbq_get_stats", "sbq_get_launch_stats", "sbq_em_solve", "sbq_set_plan",
     "sbq_set_covariates", "sbq_bias_results", "sbq_partition_lpt", "sbq_locus_devices", "sbq_synth_giant", "sbq_fetch_batch",
 ]
@@ -69,7 +73,7 @@ class Stats(ctypes.Structure):
 class LaunchStat(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int32), ("cluster_size", ctypes.c_int32), ("lanes_per_row", ctypes.c_int32),
                 ("variant", ctypes.c_int32), ("n_loci", ctypes.c_int64), ("nnz", ctypes.c_int64), ("ms", ctypes.c_double),
-                ("alg_bytes", ctypes.c_int64), ("frag_iters", ctypes.c_int64), ("max_iters", ctypes.c_int64)]
+                ("alg_bytes", ctypes.c_int64), ("frag_iters", ctypes.c_int64), ("max_iters", ctypes.c_int64), ("start_ms", ctypes.c_double)]
 
 
 _lib = None
@@ -92,7 +96,7 @@ def lib():
         L.sbq_config_default.argtypes = [ctypes.POINTER(Config)]
         L.sbq_create.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(ctypes.c_void_p)]
         L.sbq_destroy.argtypes = [ctypes.c_void_p]
-        for name in ("sbq_clear", "sbq_validate", "sbq_upload", "sbq_download"):
+        for name in ("sbq_clear", "sbq_validate", "sbq_upload", "sbq_upload_begin", "sbq_download"):
             getattr(L, name).argtypes = [ctypes.c_void_p]
         L.sbq_submit.argtypes = [ctypes.c_void_p, ctypes.POINTER(Locus), ctypes.c_int64]
         L.sbq_submit_flat.argtypes = [ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 7
@@ -256,6 +260,10 @@ class Quantifier:
     def upload(self):
         self._chk(self._L.sbq_upload(self._h))
 
+    def upload_begin(self):
+        """asynchronous upload: the next solve() overlaps the tail of the copies (arrays must stay alive until it returns)"""
+        self._chk(self._L.sbq_upload_begin(self._h))
+
     def solve(self, total_mapped_reads):
         self._chk(self._L.sbq_solve(self._h, int(total_mapped_reads)))
 
@@ -289,7 +297,7 @@ class Quantifier:
         grid = {1: "em_grid_kernel", 2: "em_grid_tma_kernel", 3: "em_grid_dual_kernel"}
         return [dict(kernel=grid.get(buf[i].variant, names[buf[i].kind]) if buf[i].kind == 3 else names[buf[i].kind], cluster_size=buf[i].cluster_size, lanes_per_row=buf[i].lanes_per_row,
                      n_loci=buf[i].n_loci, nnz=buf[i].nnz, ms=buf[i].ms, alg_bytes=buf[i].alg_bytes,
-                     frag_iters=buf[i].frag_iters, max_iters=buf[i].max_iters) for i in range(min(n, cap))]
+                     frag_iters=buf[i].frag_iters, max_iters=buf[i].max_iters, start_ms=buf[i].start_ms, threads=buf[i].lanes_per_row) for i in range(min(n, cap))]
 
     def synth_giant(self, locus_ids, rows_per_locus, seed=4, iso_lo=500, iso_hi=800, mean_extra=47.0):
         """Generate giant loci ON THE DEVICE (sbq_synth_giant): replaces submit + upload, the batch lives in HBM only."""

@@ -110,6 +110,12 @@ struct sbq_ctx {
    int device = 0;
    cudaDeviceProp prop;
    cudaStream_t stream = nullptr;
+   cudaStream_t copy_st = nullptr;                      // host -> device copies of sbq_upload*, in the order the solve needs them
+   cudaEvent_t ev_class_ready[N_SIDE_STREAMS] = {};     // weights of cluster launch i are on the device
+   cudaEvent_t ev_grid_ready = nullptr;
+   bool class_ready[N_SIDE_STREAMS] = {};               // the event above was recorded by the last upload (else: wait for ev[1], everything)
+   bool grid_ready = false;
+   bool upload_pending = false;                         // upload_begin's copies have not been waited for yet
    cudaStream_t side[N_SIDE_STREAMS] = {};
    cudaEvent_t ev[10] = {};
    cudaEvent_t ev_fork = nullptr, ev_join[N_SIDE_STREAMS] = {};
@@ -267,15 +273,16 @@ int ensure_origin(sbq_ctx* c) {
    return SBQ_SUCCESS;
 }
 
-// Single-CTA loci are bucketed by shared-memory need, and the bucket sets the THREADS of the CTA as well: the EM of a small
-// locus is a chain of short barrier-separated phases, i.e. latency-bound, so its cost in SM time is (time per iteration) x
-// (share of the SM it holds). Small CTAs let several loci share an SM (registers: 125 per thread):
-//   bucket 0  <=  12 KB   64 threads  8 per SM        bucket 3  <= 108 KB  256 threads  2 per SM
-//   bucket 1  <=  24 KB  128 threads  4 per SM        bucket 4  rest       512 threads  1 per SM
-//   bucket 2  <=  54 KB  128 threads  4 per SM
+// Single-CTA loci are bucketed by shared-memory need, and for the two smallest buckets the bucket also sets the THREADS of
+// the CTA: the EM of a small locus is a chain of short barrier-separated phases, i.e. latency-bound, so its cost in SM time is
+// (time per iteration) x (share of the SM it holds); small CTAs let several loci share an SM (registers: 125 per thread).
+// Larger single-CTA loci keep 512 threads: measured, fewer threads lengthen their iterations (159 loci of <= 54 KB: 3.1 ms
+// with 512 threads, 3.95 ms with 128) and the step is as long as its slowest locus.
+//   bucket 0  <=  12 KB   64 threads  8 per SM        bucket 2  <=  56 KB  512 threads  1 per SM (registers)
+//   bucket 1  <=  24 KB  128 threads  4 per SM        bucket 3  <= 112 KB, bucket 4: rest, 512 threads
 constexpr int N_BUCKETS = 5;
-const int BUCKET_NT[N_BUCKETS] = {64, 128, 128, 256, 512};
-int smem_bucket(size_t bytes) { return bytes <= 12 * 1024 ? 0 : bytes <= 24 * 1024 ? 1 : bytes <= 54 * 1024 ? 2 : bytes <= 108 * 1024 ? 3 : 4; }
+const int BUCKET_NT[N_BUCKETS] = {64, 128, 512, 512, 512};
+int smem_bucket(size_t bytes) { return bytes <= 12 * 1024 ? 0 : bytes <= 24 * 1024 ? 1 : bytes <= 56 * 1024 ? 2 : bytes <= 112 * 1024 ? 3 : 4; }
 
 int cluster_size_for(int64_t nnz) {
    // ~14 B of shared memory per non-zero (row part + CSC index): a CTA's slice stays under ~14k non-zeros, which still
@@ -592,6 +599,11 @@ int sbq_create(const sbq_config* cfg, sbq_ctx** out) {
    if (cfg->max_iter < 1 || !(cfg->theta_tol >= 0) || cfg->bias_mode < 0 || cfg->bias_mode > 1) return SBQ_ERR_INVALID;
    if (cfg->bias_mode == 1 && (cfg->max_out_it < 1 || cfg->max_theta_it < 1 || cfg->max_bias_it < 1 || !(cfg->bias_tol >= 0))) return SBQ_ERR_INVALID;
    if (cfg->n_gpus < 0 || cfg->n_gpus > 64) return SBQ_ERR_INVALID;
+   // A solve runs up to ~12 kernels concurrently, one stream each. The default of 8 hardware work queues makes streams share a
+   // queue, and a launch then waits behind an unrelated kernel (measured: the warp tier started 2.1 ms late behind the 8-CTA
+   // cluster launch). Only effective if the process has not created its CUDA context yet; callers that initialise CUDA first
+   // (bench.py, the tests) export the variable themselves.
+   setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
    int ndev = 0;
    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
       cudaGetLastError();
@@ -612,6 +624,10 @@ int sbq_create(const sbq_config* cfg, sbq_ctx** out) {
    if (cudaGetDeviceProperties(&c->prop, dev) != cudaSuccess) return bail(SBQ_ERR_CUDA);
    if (c->prop.major < 10) return bail(SBQ_ERR_NO_DEVICE);   // sm_100a code only
    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SBQ_ERR_CUDA);
+   if (cudaStreamCreateWithFlags(&c->copy_st, cudaStreamNonBlocking) != cudaSuccess) return bail(SBQ_ERR_CUDA);
+   if (cudaEventCreateWithFlags(&c->ev_grid_ready, cudaEventDisableTiming) != cudaSuccess) return bail(SBQ_ERR_CUDA);
+   for (auto& e : c->ev_class_ready)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(SBQ_ERR_CUDA);
    for (auto& s : c->side)
       if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return bail(SBQ_ERR_CUDA);
    for (auto& e : c->ev)
@@ -636,6 +652,7 @@ void sbq_destroy(sbq_ctx* c) {
    if (!c) return;
    multi_destroy(c);
    cudaSetDevice(c->device);
+   if (c->copy_st) cudaStreamSynchronize(c->copy_st);
    if (c->stream) cudaStreamSynchronize(c->stream);
    c->h_loc_row_off.release(); c->h_loc_iso_off.release(); c->h_row_ptr.release();
    c->h_col.release(); c->h_count.release(); c->h_iso_len.release(); c->h_alpha.release();
@@ -650,6 +667,9 @@ void sbq_destroy(sbq_ctx* c) {
    for (auto& e : c->ev_join) if (e) cudaEventDestroy(e);
    for (auto& t : c->lt) { if (t.e0) cudaEventDestroy(t.e0); if (t.e1) cudaEventDestroy(t.e1); }
    for (auto& s : c->side) if (s) cudaStreamDestroy(s);
+   if (c->ev_grid_ready) cudaEventDestroy(c->ev_grid_ready);
+   for (auto& e : c->ev_class_ready) if (e) cudaEventDestroy(e);
+   if (c->copy_st) cudaStreamDestroy(c->copy_st);
    if (c->stream) cudaStreamDestroy(c->stream);
    delete c;
 }
@@ -668,6 +688,11 @@ int sbq_set_plan(sbq_ctx* c, int force_tier, int force_cluster) {
 int sbq_clear(sbq_ctx* c) {
    if (!c) return SBQ_ERR_INVALID;
    std::lock_guard<std::mutex> lk(c->mu);
+   if (c->upload_pending) {   // copies of an asynchronous upload still read the host arrays
+      cudaSetDevice(c->device);
+      cudaStreamSynchronize(c->copy_st);
+      c->upload_pending = false;
+   }
    reset_batch(c);
    return SBQ_SUCCESS;
 }
@@ -755,11 +780,21 @@ int sbq_validate(sbq_ctx* c) {
    return SBQ_SUCCESS;
 }
 
-int sbq_upload(sbq_ctx* c) {
-   if (!c) return SBQ_ERR_INVALID;
-   if (c->multi) return multi_upload(c);
-   std::lock_guard<std::mutex> lk(c->mu);
+} // extern "C" (reopened below)
+
+// Host -> device copies of the staged batch, ENQUEUED in the order the solve needs them (caller holds c->mu):
+//   1. offsets, row pointers, counts, lengths and ALL columns in bulk - while they move, the host plans the tiers;
+//   2. the weights (two thirds of the bytes) locus by locus for the launches on the critical path: giant loci, then the
+//      cluster-tier launches of 8 and 16 CTAs per locus (a few dozen large loci), one "ready" event per launch;
+//   3. the weights of everything else (the gaps between the ranges of step 2).
+// sbq_solve makes every launch wait for its own event only, so the largest loci start iterating while the rest of the batch
+// is still crossing PCIe. Nothing is synchronised here: the host arrays must stay valid until upload_finish / the solve.
+static int upload_begin(sbq_ctx* c) {
    CU(cudaSetDevice(c->device));
+   if (c->upload_pending) {
+      CU(cudaStreamSynchronize(c->copy_st));
+      c->upload_pending = false;
+   }
    if (c->n_loci == 0) return fail(c, SBQ_ERR_STATE, "nothing submitted");
    if (c->host_released) return fail(c, SBQ_ERR_STATE, "the borrowed batch was released by the previous sbq_upload: sbq_clear and submit again");
    {
@@ -771,41 +806,113 @@ int sbq_upload(sbq_ctx* c) {
    int32_t *d_col = const_cast<int32_t*>(dp.col), *d_cnt = const_cast<int32_t*>(dp.count), *d_il = const_cast<int32_t*>(dp.iso_len);
    double* d_al = const_cast<double*>(dp.alpha);
 
-   cudaStream_t st = c->stream;
+   cudaStream_t st = c->copy_st;
+   c->upload_pending = true;
+   c->resident = c->solved = c->downloaded = false;
    CU(cudaEventRecord(c->ev[0], st));
    CU(cudaMemcpyAsync(d_lro, loc_row_off(c), (c->n_loci + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
    CU(cudaMemcpyAsync(d_lio, loc_iso_off(c), (c->n_loci + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
    CU(cudaMemcpyAsync(d_rp, row_ptr(c), (c->n_row + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-   if (c->nnz) {
-      CU(cudaMemcpyAsync(d_col, colp(c), c->nnz * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-      CU(cudaMemcpyAsync(d_al, alphap(c), c->nnz * sizeof(double), cudaMemcpyHostToDevice, st));
-   }
    if (c->n_row) CU(cudaMemcpyAsync(d_cnt, countp(c), c->n_row * sizeof(int32_t), cudaMemcpyHostToDevice, st));
    CU(cudaMemcpyAsync(d_il, iso_lenp(c), c->n_iso * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-   // the tier plan (O(loci + rows) on the host) is made while the DMA engine moves the batch
+   if (c->nnz) CU(cudaMemcpyAsync(d_col, colp(c), c->nnz * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+   // the tier plan (O(loci + rows) on the host) is made while the DMA engine moves the first ~40 % of the bytes
    {
       capture_meta_host(c);
       const int rc = plan(c);
       if (rc) {
          cudaStreamSynchronize(st);
+         c->upload_pending = false;
          return rc;
       }
    }
    if (c->h_lists.n) CU(cudaMemcpyAsync(c->d_lists_p, c->h_lists.p, c->h_lists.n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-   CU(cudaEventRecord(c->ev[1], st));
+   // weights in priority order
+   const int64_t* lro = loc_row_off(c);
+   const int64_t* rp = row_ptr(c);
+   const double* al = alphap(c);
+   std::vector<std::pair<int64_t, int64_t>> done;   // [k0, k1) ranges already enqueued
+   auto copy_loci = [&](const std::vector<int32_t>& loci) -> int {
+      for (int32_t l : loci) {
+         const int64_t k0 = rp[lro[l]], k1 = rp[lro[l + 1]];
+         if (k1 > k0) {
+            CU(cudaMemcpyAsync(d_al + k0, al + k0, (size_t)(k1 - k0) * sizeof(double), cudaMemcpyHostToDevice, st));
+            done.emplace_back(k0, k1);
+         }
+      }
+      return SBQ_SUCCESS;
+   };
+   for (auto& r : c->class_ready) r = false;
+   c->grid_ready = false;
+   if (!c->grid_list.empty() && c->grid_list.size() <= 16) {
+      const int rc = copy_loci(c->grid_list);
+      if (rc) return rc;
+      CU(cudaEventRecord(c->ev_grid_ready, st));
+      c->grid_ready = true;
+   }
+   // Only launches of a few LARGE loci are worth their own copies: a copy costs ~6 us of DMA set-up whatever its size (measured:
+   // 1150 per-locus copies took 7.3 ms for the 66 MB that seven bulk copies move in 1.5 ms).
+   size_t n_prio = 0;
+   for (size_t i = 0; i < c->classes.size() && i < (size_t)N_SIDE_STREAMS; ++i) {
+      if (c->classes[i].cs < 8 || n_prio + c->classes[i].loci.size() > 48) continue;   // the rest goes with the bulk of step 3
+      n_prio += c->classes[i].loci.size();
+      const int rc = copy_loci(c->classes[i].loci);
+      if (rc) return rc;
+      CU(cudaEventRecord(c->ev_class_ready[i], st));
+      c->class_ready[i] = true;
+   }
+   std::sort(done.begin(), done.end());
+   int64_t pos = 0;
+   for (size_t i = 0; i <= done.size(); ++i) {
+      const int64_t end = i < done.size() ? done[i].first : c->nnz;
+      if (end > pos) CU(cudaMemcpyAsync(d_al + pos, al + pos, (size_t)(end - pos) * sizeof(double), cudaMemcpyHostToDevice, st));
+      if (i < done.size()) pos = std::max(pos, done[i].second);
+   }
+   CU(cudaEventRecord(c->ev[1], st));   // everything is on the device when this fires
    if (!c->classes.empty()) {
       // L2-resident overflow of the cluster tier's transposed index (4 B per non-zero, indexed like col/alpha)
       if (!c->d_csc.reserve(align_up(c->nnz * 4 + 16))) return fail(c, SBQ_ERR_NOMEM, "device allocation failed (transposed-index scratch)");
       dp.csc = (unsigned*)c->d_csc.p;
    }
-   CU(cudaStreamSynchronize(st));   // borrowed host arrays may be released after this returns
+   c->stats.h2d_bytes = 2 * (c->n_loci + 1) * 8 + (c->n_row + 1) * 8 + c->nnz * 12 + c->n_row * 4 + c->n_iso * 4 + (int64_t)c->h_lists.n * 4;
+   c->stats.n_loci = c->n_loci; c->stats.n_row = c->n_row; c->stats.n_iso = c->n_iso; c->stats.nnz = c->nnz;
+   c->stats.weights_ms = 0.0;
+   c->col16_ready = false;
+   c->resident = true;                  // the solve may be enqueued: its launches wait for the "ready" events
+   return SBQ_SUCCESS;
+}
+
+// wait for the copies of upload_begin (the caller's arrays may be released afterwards) and record the upload time
+static int upload_wait(sbq_ctx* c) {
+   if (!c->upload_pending) return SBQ_SUCCESS;
+   CU(cudaSetDevice(c->device));
+   CU(cudaStreamSynchronize(c->copy_st));
+   c->upload_pending = false;
    if (c->borrowed) c->host_released = true;   // from here on nothing reads the caller's arrays (metric accounting uses c->meta)
    float ms = 0;
    CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
    c->stats.upload_ms = ms;
-   c->stats.h2d_bytes = 2 * (c->n_loci + 1) * 8 + (c->n_row + 1) * 8 + c->nnz * 12 + c->n_row * 4 + c->n_iso * 4 + (int64_t)c->h_lists.n * 4;
-   c->stats.n_loci = c->n_loci; c->stats.n_row = c->n_row; c->stats.n_iso = c->n_iso; c->stats.nnz = c->nnz;
-   c->stats.weights_ms = 0.0;
+   return SBQ_SUCCESS;
+}
+
+extern "C" {
+
+int sbq_upload_begin(sbq_ctx* c) {
+   if (!c) return SBQ_ERR_INVALID;
+   if (c->multi || c->deferred == 1 || c->cfg.bias_mode == 1) return sbq_upload(c);   // these paths have extra stages: synchronous upload
+   std::lock_guard<std::mutex> lk(c->mu);
+   return upload_begin(c);
+}
+
+int sbq_upload(sbq_ctx* c) {
+   if (!c) return SBQ_ERR_INVALID;
+   if (c->multi) return multi_upload(c);
+   std::lock_guard<std::mutex> lk(c->mu);
+   {
+      int rc = upload_begin(c);
+      if (!rc) rc = upload_wait(c);   // borrowed host arrays may be released after this returns
+      if (rc) return rc;
+   }
    if (c->deferred == 1) {
       // alpha on the GPU: upload the per-entry descriptors and the insert model, one warp per CSR entry
       if (!c->have_model) return fail(c, SBQ_ERR_STATE, "deferred weights need sbq_set_insert_model()");
@@ -916,7 +1023,9 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
    // grid tier on the main stream first (it owns the whole GPU while it runs)
    c->stats.grid_em_ms = 0;
    for (auto& t : c->lt) t.used = false;
+   const bool pending = c->upload_pending;   // asynchronous upload in flight: every launch waits for the copies it needs only
    if (!c->grid_list.empty()) {
+      if (pending) CU(cudaStreamWaitEvent(st, c->grid_ready ? c->ev_grid_ready : c->ev[1], 0));
       CU(cudaEventRecord(c->ev[6], st));
       int n_launch = 0;
       int rc = 0;
@@ -957,6 +1066,7 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
    for (auto& lc : c->classes) {
       cudaStream_t ss = serialize ? st : c->side[used_side % N_SIDE_STREAMS];
       if (!serialize && used_side < N_SIDE_STREAMS) CU(cudaStreamWaitEvent(ss, c->ev_fork, 0));
+      if (pending) CU(cudaStreamWaitEvent(ss, (used_side < N_SIDE_STREAMS && c->class_ready[used_side]) ? c->ev_class_ready[used_side] : c->ev[1], 0));
       LaunchTimer& t = c->lt[2 + used_side % N_SIDE_STREAMS];
       CU(cudaEventRecord(t.e0, ss));
       // register caps (launch bounds) follow the CTAs-per-SM targets of the buckets
@@ -976,6 +1086,7 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
       CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_warp_kernel, WT_WARPS * 32, smem));
       const int grid = std::max(1, std::min((n + WT_WARPS - 1) / WT_WARPS, per_sm * c->prop.multiProcessorCount));
       int* queue = (int*)((char*)c->d_fpkm_sum + 64);
+      if (pending) CU(cudaStreamWaitEvent(st, c->ev[1], 0));   // many small loci all over the batch: they need everything
       CU(cudaMemsetAsync(queue, 0, sizeof(int), st));
       CU(cudaEventRecord(c->lt[0].e0, st));
       em_warp_kernel<<<grid, WT_WARPS * 32, smem, st>>>(c->dp, c->d_lists_p + c->warp_list_off, n, c->warp_max_iso, queue);
@@ -994,6 +1105,10 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
    ++launches;
    CU(cudaEventRecord(c->ev[4], st));
    CU(cudaStreamSynchronize(st));
+   if (pending) {
+      const int rcw = upload_wait(c);   // complete by now (the last launches waited for it): records the upload time, releases the host arrays
+      if (rcw) return rcw;
+   }
    float ms = 0;
    CU(cudaEventElapsedTime(&ms, c->ev[2], c->ev[4]));
    c->stats.solve_ms = ms;
@@ -1006,18 +1121,20 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
    // per-launch records: [warp] [grid] [cluster classes...]
    c->launch_stats.clear();
    c->locus_launch.assign(c->n_loci, -1);
-   auto add_stat = [&](int kind, int cs, int lpr, const std::vector<int32_t>& loci, double ms_) {
+   auto add_stat = [&](int kind, int cs, int lpr, const std::vector<int32_t>& loci, double ms_, cudaEvent_t e0 = nullptr) {
       sbq_launch_stat ls{};
       ls.kind = kind; ls.cluster_size = cs; ls.lanes_per_row = lpr; ls.n_loci = (int64_t)loci.size(); ls.ms = ms_;
+      float st_ms = 0;
+      if (e0 && cudaEventElapsedTime(&st_ms, c->ev[2], e0) == cudaSuccess) ls.start_ms = st_ms;
       for (int32_t l : loci) c->locus_launch[l] = (int32_t)c->launch_stats.size();
       c->launch_stats.push_back(ls);
    };
-   if (c->lt[0].used) { CU(cudaEventElapsedTime(&ms, c->lt[0].e0, c->lt[0].e1)); add_stat(1, 1, 1, c->warp_list, ms); }
-   if (!c->grid_list.empty()) { add_stat(3, 0, 32, c->grid_list, c->stats.grid_em_ms); c->launch_stats.back().variant = c->grid_variant; }
+   if (c->lt[0].used) { CU(cudaEventElapsedTime(&ms, c->lt[0].e0, c->lt[0].e1)); add_stat(1, 1, 1, c->warp_list, ms, c->lt[0].e0); }
+   if (!c->grid_list.empty()) { add_stat(3, 0, 32, c->grid_list, c->stats.grid_em_ms, c->ev[6]); c->launch_stats.back().variant = c->grid_variant; }
    for (size_t i = 0; i < c->classes.size(); ++i) {
       LaunchTimer& t = c->lt[2 + i % N_SIDE_STREAMS];
       CU(cudaEventElapsedTime(&ms, t.e0, t.e1));
-      add_stat(2, c->classes[i].cs, c->classes[i].lpr, c->classes[i].loci, ms);
+      add_stat(2, c->classes[i].cs, c->classes[i].lpr, c->classes[i].loci, ms, t.e0);
    }
    c->stats.kernel_launches = launches;
    c->solved = true;
@@ -1107,7 +1224,7 @@ int sbq_download(sbq_ctx* c) {
 }
 
 int sbq_run(sbq_ctx* c, int64_t total_mapped_reads) {
-   int rc = sbq_upload(c);
+   int rc = sbq_upload_begin(c);   // the solve overlaps the tail of the copies (synchronous for multi-GPU / deferred / bias batches)
    if (rc) return rc;
    if ((rc = sbq_solve(c, total_mapped_reads))) return rc;
    if (c->multi) {   // N devices: one ncclAllReduce of the FPKM sums, TPM from the device copy of the result
@@ -1337,6 +1454,7 @@ int sbq_fetch_batch(sbq_ctx* c, int64_t* loc_row_off_, int64_t* loc_iso_off_, in
    std::lock_guard<std::mutex> lk(c->mu);
    CU(cudaSetDevice(c->device));
    if (!c->resident) return fail(c, SBQ_ERR_STATE, "sbq_fetch_batch before sbq_upload / sbq_synth_giant");
+   { const int rcw = upload_wait(c); if (rcw) return rcw; }
    cudaStream_t st = c->stream;
    if (loc_row_off_) CU(cudaMemcpyAsync(loc_row_off_, c->dp.loc_row_off, (c->n_loci + 1) * 8, cudaMemcpyDeviceToHost, st));
    if (loc_iso_off_) CU(cudaMemcpyAsync(loc_iso_off_, c->dp.loc_iso_off, (c->n_loci + 1) * 8, cudaMemcpyDeviceToHost, st));
@@ -1355,6 +1473,7 @@ int sbq_fetch_alpha(sbq_ctx* c, double* alpha) {
    std::lock_guard<std::mutex> lk(c->mu);
    CU(cudaSetDevice(c->device));
    if (!c->resident) return fail(c, SBQ_ERR_STATE, "sbq_fetch_alpha before sbq_upload");
+   { const int rcw = upload_wait(c); if (rcw) return rcw; }
    CU(cudaMemcpyAsync(alpha, c->dp.alpha, c->nnz * 8, cudaMemcpyDeviceToHost, c->stream));
    CU(cudaStreamSynchronize(c->stream));
    return SBQ_SUCCESS;

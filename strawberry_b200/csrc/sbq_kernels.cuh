@@ -107,8 +107,8 @@ __device__ __forceinline__ unsigned trace_smid() { unsigned s; asm volatile("mov
 #endif
 constexpr int WT_WARPS = 8;
 constexpr int WT_MAX_ISO = 32;
-constexpr int WT_MAX_ROWS = 256;   // planner: loci a warp still takes (a lane then walks up to 8 rows per iteration)
-constexpr int WT_MAX_NNZ = 1024;
+constexpr int WT_MAX_ROWS = 64;    // planner: loci a warp still takes (a lane then walks two rows per iteration); measured: with 256 rows /
+constexpr int WT_MAX_NNZ = 256;    // 1024 non-zeros the warp tier's longest locus takes 3.1 ms (8 rows per lane from L1/L2 every iteration)
 constexpr int WT_STRIDE = 33;
 
 __host__ __device__ inline size_t warp_tier_smem_bytes(int max_iso) {
