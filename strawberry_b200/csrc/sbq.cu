@@ -7,6 +7,7 @@
 // LocusContext::estimate_abundances -> EmSolver (reference src/alignments.cpp:1756-1829,
 // src/estimate.cpp:279-488). There is no CPU fallback in this file by design.
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -188,6 +189,8 @@ struct sbq_ctx {
    // results (host, pinned)
    PinnedVec<double> r_theta, r_fpkm, r_frac, r_tpm, r_locus_fpkm;
    PinnedVec<int32_t> r_keep, r_iters, r_status;
+   PinnedVec<long long> r_frags;   // fragment total per locus (device sum, metric accounting)
+   DevBuf d_frags;
    double r_fpkm_sum = 0.0;
 
    sbq_stats stats{};
@@ -307,15 +310,12 @@ int cluster_size_for(int64_t nnz) {
 
 // ---- planner: tier per locus, launch classes, work lists sorted by descending size -------------
 // per-locus shape and fragment total from the staged host arrays (while they are still valid)
+// (the fragment totals, an O(rows) sum, are taken on the device by locus_frags_kernel and filled in by upload_wait)
 void capture_meta_host(sbq_ctx* c) {
    const int64_t *lro = loc_row_off(c), *lio = loc_iso_off(c), *rp = row_ptr(c);
-   const int32_t* cnt = countp(c);
    c->meta.resize((size_t)c->n_loci);
-   for (int64_t l = 0; l < c->n_loci; ++l) {
-      int64_t frags = 0;
-      for (int64_t i = lro[l]; i < lro[l + 1]; ++i) frags += cnt[i];
-      c->meta[l] = {rp[lro[l + 1]] - rp[lro[l]], frags, (int32_t)(lro[l + 1] - lro[l]), (int32_t)(lio[l + 1] - lio[l])};
-   }
+   for (int64_t l = 0; l < c->n_loci; ++l)
+      c->meta[l] = {rp[lro[l + 1]] - rp[lro[l]], 0, (int32_t)(lro[l + 1] - lro[l]), (int32_t)(lio[l + 1] - lio[l])};
 }
 
 // works from c->meta only, so that batches that exist only on the device (sbq_synth_giant) are planned the same way
@@ -388,7 +388,21 @@ int plan(sbq_ctx* c) {
       }
    }
    auto by_size = [&](int32_t a, int32_t b) { return nnz_of[a] != nnz_of[b] ? nnz_of[a] > nnz_of[b] : a < b; };
-   std::sort(c->warp_list.begin(), c->warp_list.end(), by_size);
+   {
+      // warp-tier work list by descending non-zeros (ties by index): a counting sort - the keys are <= WT_MAX_NNZ unless the
+      // tier was forced, and a comparison sort of ~18 k indirect keys costs more host time than the rest of the plan together
+      bool small_keys = true;
+      for (int32_t l : c->warp_list) small_keys &= nnz_of[l] <= WT_MAX_NNZ;
+      if (small_keys) {
+         std::vector<int32_t> first(WT_MAX_NNZ + 2, 0), sorted(c->warp_list.size());
+         for (int32_t l : c->warp_list) ++first[WT_MAX_NNZ - (int)nnz_of[l] + 1];
+         for (int k = 1; k <= WT_MAX_NNZ + 1; ++k) first[k] += first[k - 1];
+         for (int32_t l : c->warp_list) sorted[first[WT_MAX_NNZ - (int)nnz_of[l]]++] = l;   // the list is in ascending index order: stable
+         c->warp_list.swap(sorted);
+      } else {
+         std::sort(c->warp_list.begin(), c->warp_list.end(), by_size);
+      }
+   }
    // two-slot-kernel loci first, each part by descending size
    std::sort(c->grid_list.begin(), c->grid_list.end(), [&](int32_t a, int32_t b) { return dual_locus[a] != dual_locus[b] ? dual_locus[a] > dual_locus[b] : by_size(a, b); });
    c->grid_n_dual = 0;
@@ -658,7 +672,7 @@ void sbq_destroy(sbq_ctx* c) {
    c->h_col.release(); c->h_count.release(); c->h_iso_len.release(); c->h_alpha.release();
    c->h_lists.release();
    c->r_theta.release(); c->r_fpkm.release(); c->r_frac.release(); c->r_tpm.release();
-   c->r_locus_fpkm.release(); c->r_keep.release(); c->r_iters.release(); c->r_status.release();
+   c->r_locus_fpkm.release(); c->r_keep.release(); c->r_iters.release(); c->r_status.release(); c->r_frags.release(); c->d_frags.release();
    c->d_in.release(); c->d_out.release(); c->d_lists.release(); c->d_grid_scratch.release(); c->d_col16.release(); c->d_rowrec.release(); c->d_csc.release(); c->d_synth.release(); c->d_bias.release();
    c->h_cov.release(); c->r_beta.release(); c->r_outer.release();
    c->h_wseg.release(); c->h_wn.release(); c->h_wmask.release(); c->h_wpool.release(); c->h_wlen.release(); c->h_wpool_off.release(); c->d_weights.release();
@@ -815,7 +829,14 @@ static int upload_begin(sbq_ctx* c) {
    CU(cudaMemcpyAsync(d_rp, row_ptr(c), (c->n_row + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
    if (c->n_row) CU(cudaMemcpyAsync(d_cnt, countp(c), c->n_row * sizeof(int32_t), cudaMemcpyHostToDevice, st));
    CU(cudaMemcpyAsync(d_il, iso_lenp(c), c->n_iso * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+   // fragment total of every locus (metric accounting only), summed on the device from the counts that just arrived
+   if (!c->r_frags.reserve((size_t)c->n_loci) || !c->d_frags.reserve(align_up((size_t)c->n_loci * 8))) return fail(c, SBQ_ERR_NOMEM, "fragment-total buffers");
+   locus_frags_kernel<<<std::max(1, std::min<int>((int)((c->n_loci + 7) / 8), c->prop.multiProcessorCount * 8)), 256, 0, st>>>(d_lro, d_cnt, c->n_loci, (long long*)c->d_frags.p);
+   CU(cudaGetLastError());
+   CU(cudaMemcpyAsync(c->r_frags.p, c->d_frags.p, (size_t)c->n_loci * 8, cudaMemcpyDeviceToHost, st));
    if (c->nnz) CU(cudaMemcpyAsync(d_col, colp(c), c->nnz * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+   const bool timing = getenv("SBQ_TIMING") != nullptr;
+   const auto t_plan0 = std::chrono::steady_clock::now();
    // the tier plan (O(loci + rows) on the host) is made while the DMA engine moves the first ~40 % of the bytes
    {
       capture_meta_host(c);
@@ -826,6 +847,7 @@ static int upload_begin(sbq_ctx* c) {
          return rc;
       }
    }
+   if (timing) fprintf(stderr, "SBQ_TIMING plan_ms %.3f\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan0).count());
    if (c->h_lists.n) CU(cudaMemcpyAsync(c->d_lists_p, c->h_lists.p, c->h_lists.n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
    // weights in priority order
    const int64_t* lro = loc_row_off(c);
@@ -889,6 +911,7 @@ static int upload_wait(sbq_ctx* c) {
    CU(cudaStreamSynchronize(c->copy_st));
    c->upload_pending = false;
    if (c->borrowed) c->host_released = true;   // from here on nothing reads the caller's arrays (metric accounting uses c->meta)
+   for (size_t l = 0; l < c->meta.size(); ++l) c->meta[l].frags = c->r_frags.p[l];
    float ms = 0;
    CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
    c->stats.upload_ms = ms;

@@ -1353,6 +1353,18 @@ __global__ void tpm_kernel(const double* __restrict__ fpkm, double* __restrict__
    if (i < n) tpm[i] = 1e6 * fpkm[i] / total;
 }
 
+// fragment total of every locus (sum of its class counts): one warp per locus. Only the benchmark metric needs it.
+__global__ void __launch_bounds__(256) locus_frags_kernel(const int64_t* __restrict__ loc_row_off, const int32_t* __restrict__ count, int64_t n_loci, long long* __restrict__ out) {
+   const int lane = threadIdx.x & 31;
+   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+   for (int64_t l = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; l < n_loci; l += nw) {
+      long long v = 0;
+      for (int64_t i = loc_row_off[l] + lane; i < loc_row_off[l + 1]; i += 32) v += count[i];
+      v = warp_sum_ll(v);
+      if (lane == 0) out[l] = v;
+   }
+}
+
 // same, with the denominator read from device memory (multi-GPU: the all-reduced sum never visits the host)
 __global__ void tpm_dev_kernel(const double* __restrict__ fpkm, double* __restrict__ tpm, int64_t n, const double* __restrict__ total) {
    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
