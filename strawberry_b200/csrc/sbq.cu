@@ -36,6 +36,9 @@ namespace {
 
 constexpr size_t SMEM_CAP = CL_SMEM_CAP;   // dynamic shared memory we ask for at most (227 KB usable)
 constexpr int N_SIDE_STREAMS = 12;
+#ifndef SBQ_DEFAULT_ORDER
+#define SBQ_DEFAULT_ORDER 0
+#endif
 
 // ---- pinned host array with geometric growth -------------------------------------------------
 template <typename T>
@@ -292,7 +295,7 @@ int cluster_size_for(int64_t nnz) {
    // fits with its CSC index. Smaller clusters cost latency per iteration (fewer SMs per locus) but less SM time in
    // total; these thresholds were the best of a sweep on the human-shaped workload (profiles/r01_cluster_thresholds.txt).
    // SBQ_CS_THRESH="a,b,c,d" (thousands of non-zeros) overrides the four thresholds (tuning aid).
-   static int64_t th[4] = {12 * 1024, 24 * 1024, 48 * 1024, 112 * 1024};
+   static int64_t th[4] = {16 * 1024, 32 * 1024, 64 * 1024, 150 * 1024};
    static bool init = false;
    if (!init) {
       init = true;
@@ -404,7 +407,15 @@ int plan(sbq_ctx* c) {
       }
    }
    // two-slot-kernel loci first, each part by descending size
-   std::sort(c->grid_list.begin(), c->grid_list.end(), [&](int32_t a, int32_t b) { return dual_locus[a] != dual_locus[b] ? dual_locus[a] > dual_locus[b] : by_size(a, b); });
+   // (within the two-slot part: by the warp count the locus' own T allows, so that every launch group is homogeneous)
+   std::sort(c->grid_list.begin(), c->grid_list.end(), [&](int32_t a, int32_t b) {
+      if (dual_locus[a] != dual_locus[b]) return dual_locus[a] > dual_locus[b];
+      if (dual_locus[a]) {
+         const int na = grid_dual_nc(c->meta[a].T), nb_ = grid_dual_nc(c->meta[b].T);
+         if (na != nb_) return na > nb_;
+      }
+      return by_size(a, b);
+   });
    c->grid_n_dual = 0;
    for (int32_t l : c->grid_list) c->grid_n_dual += dual_locus[l];
    c->grid_rec_off.assign(c->grid_n_dual + 1, 0);
@@ -1058,7 +1069,9 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
       if (n_dual) {
          GridDualBufs bf{&c->d_grid_scratch.p, &c->d_grid_scratch.cap, &c->d_col16.p, &c->d_col16.cap, &c->d_rowrec.p, &c->d_rowrec.cap};
          int nl = 0;
-         rc = grid_dual_launch(c->dp, c->nnz, d_grid, n_dual, c->grid_max_iso_dual, c->grid_rec_off.data(), c->prop, bf, c->col16_ready, st, &nl);
+         std::vector<int> h_iso((size_t)n_dual);
+         for (int i = 0; i < n_dual; ++i) h_iso[i] = c->meta[c->grid_list[i]].T;
+         rc = grid_dual_launch(c->dp, c->nnz, d_grid, n_dual, h_iso.data(), c->grid_rec_off.data(), c->prop, bf, c->col16_ready, st, &nl);
          n_launch += nl;
          c->grid_variant = 3;
       }
@@ -1086,22 +1099,27 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
       CU(cudaEventRecord(c->ev[7], st));
    }
    const bool serialize = getenv("SBQ_SERIALIZE") != nullptr;   // debugging / profiling: one stream, isolated kernel times
-   for (auto& lc : c->classes) {
-      cudaStream_t ss = serialize ? st : c->side[used_side % N_SIDE_STREAMS];
-      if (!serialize && used_side < N_SIDE_STREAMS) CU(cudaStreamWaitEvent(ss, c->ev_fork, 0));
-      if (pending) CU(cudaStreamWaitEvent(ss, (used_side < N_SIDE_STREAMS && c->class_ready[used_side]) ? c->ev_class_ready[used_side] : c->ev[1], 0));
-      LaunchTimer& t = c->lt[2 + used_side % N_SIDE_STREAMS];
-      CU(cudaEventRecord(t.e0, ss));
-      // register caps (launch bounds) follow the CTAs-per-SM targets of the buckets
-      int rc = lc.lpr == 64 ? launch_cluster_class_nt<64, 0, 8>(c, lc, ss) : lc.lpr == 128 ? launch_cluster_class_nt<128, 0, 4>(c, lc, ss) :
-               lc.lpr == 256 ? launch_cluster_class_nt<256, 0, 2>(c, lc, ss) : launch_cluster_class_nt<CL_NT, 0, 1>(c, lc, ss);
-      if (rc) return rc;
-      CU(cudaEventRecord(t.e1, ss));
-      t.used = true;
-      ++used_side;
-      ++launches;
+   // Launch ORDER (class i keeps stream / timer / ready-event i whatever its position). The work distributor serves
+   // kernels roughly in launch order, 16- and 8-CTA clusters strand a few SMs per GPC that only single CTAs can use, and the
+   // many small loci have critical paths of their own (~1 ms): see DESIGN.md section 5 for the measured timelines.
+   static const int order_mode = getenv("SBQ_ORDER") ? atoi(getenv("SBQ_ORDER")) : SBQ_DEFAULT_ORDER;
+   const int ncls = (int)c->classes.size();
+   std::vector<int> ord;
+   int warp_pos = ncls;   // position in ord before which the warp tier is launched
+   {
+      std::vector<int> big, small, rest;
+      for (int i = 0; i < ncls; ++i) {
+         const LaunchClass& lc = c->classes[i];
+         if (lc.lpr < CL_NT) small.push_back(i);
+         else if (lc.cs >= (order_mode == 3 ? 16 : 8)) big.push_back(i);
+         else rest.push_back(i);
+      }
+      if (order_mode == 1) { ord = small; ord.insert(ord.end(), big.begin(), big.end()); ord.insert(ord.end(), rest.begin(), rest.end()); warp_pos = 0; }
+      else if (order_mode == 2 || order_mode == 3) { ord = big; warp_pos = (int)ord.size(); ord.insert(ord.end(), small.begin(), small.end()); ord.insert(ord.end(), rest.begin(), rest.end()); }
+      else { for (int i = 0; i < ncls; ++i) ord.push_back(i); }
    }
-   if (!c->warp_list.empty()) {
+   auto launch_warp = [&]() -> int {
+      if (c->warp_list.empty()) return SBQ_SUCCESS;
       const size_t smem = warp_tier_smem_bytes(c->warp_max_iso);
       CU(cudaFuncSetAttribute(em_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       const int n = (int)c->warp_list.size();
@@ -1117,7 +1135,30 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
       CU(cudaEventRecord(c->lt[0].e1, st));
       c->lt[0].used = true;
       ++launches;
+      return SBQ_SUCCESS;
+   };
+   for (int pos = 0; pos <= ncls; ++pos) {
+      if (pos == warp_pos) {
+         const int rcw = launch_warp();
+         if (rcw) return rcw;
+      }
+      if (pos == ncls) break;
+      const int i = ord[pos];
+      const LaunchClass& lc = c->classes[i];
+      cudaStream_t ss = serialize ? st : c->side[i % N_SIDE_STREAMS];
+      if (!serialize && i < N_SIDE_STREAMS) CU(cudaStreamWaitEvent(ss, c->ev_fork, 0));
+      if (pending) CU(cudaStreamWaitEvent(ss, (i < N_SIDE_STREAMS && c->class_ready[i]) ? c->ev_class_ready[i] : c->ev[1], 0));
+      LaunchTimer& t = c->lt[2 + i % N_SIDE_STREAMS];
+      CU(cudaEventRecord(t.e0, ss));
+      // register caps (launch bounds) follow the CTAs-per-SM targets of the buckets
+      int rc = lc.lpr == 64 ? launch_cluster_class_nt<64, 0, 8>(c, lc, ss) : lc.lpr == 128 ? launch_cluster_class_nt<128, 0, 4>(c, lc, ss) :
+               lc.lpr == 256 ? launch_cluster_class_nt<256, 0, 2>(c, lc, ss) : launch_cluster_class_nt<CL_NT, 0, 1>(c, lc, ss);
+      if (rc) return rc;
+      CU(cudaEventRecord(t.e1, ss));
+      t.used = true;
+      ++launches;
    }
+   used_side = ncls;
    for (int i = 0; i < std::min(used_side, N_SIDE_STREAMS) && !serialize; ++i) {
       CU(cudaEventRecord(c->ev_join[i], c->side[i]));
       CU(cudaStreamWaitEvent(st, c->ev_join[i], 0));
@@ -1601,6 +1642,21 @@ int sbq_em_solve(sbq_ctx* c, const sbq_locus* locus, double* theta, int32_t* ite
    if (iters) *iters = it;
    return st;
 }
+
+#ifdef SBQ_TRACE
+// debug builds only (not part of the ABI header): copy out and reset the CTA timeline; 4 words per record, returns the count
+int sbq_debug_trace(unsigned long long* out, int cap) {
+   unsigned n = 0;
+   cudaDeviceSynchronize();
+   cudaMemcpyFromSymbol(&n, sbq::g_trace_n, sizeof n);
+   if (n > sbq::TRACE_CAP) n = sbq::TRACE_CAP;
+   if ((int)n > cap) n = (unsigned)cap;
+   if (n) cudaMemcpyFromSymbol(out, sbq::g_trace, (size_t)n * 32);
+   const unsigned zero = 0;
+   cudaMemcpyToSymbol(sbq::g_trace_n, &zero, sizeof zero);
+   return (int)n;
+}
+#endif
 
 // page-locked host memory for callers that want sbq_submit_flat to use their arrays in place
 void* sbq_host_alloc(size_t bytes) {

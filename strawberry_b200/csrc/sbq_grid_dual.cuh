@@ -79,7 +79,9 @@ struct G6Cfg {
    static constexpr int STAGE_BYTES = ((R_OFF + R_BYTES + 127) / 128) * 128;
    static size_t fixed_bytes(int T) { return (size_t)(2 * g6_tp(T) + 64) * (1 + NC) * sizeof(double); }   // th2[2Tp+64] | acc[NC][2Tp+64]
    static int stages_per_warp(int T) {   // ring depth per warp that fits beside the accumulators
-      const long long room = 225LL * 1024 - (long long)fixed_bytes(T);
+      // 227 KB usable per CTA (232 448 B) minus the kernel's static shared memory (640 B) and a little slack: T = 800 still gets
+      // twelve warps (173 056 B of theta + accumulators + 12 x 4 864 B of stages)
+      const long long room = 231680LL - (long long)fixed_bytes(T);
       long long spw = room / ((long long)STAGE_BYTES * NC);
       if (spw > G6_MAX_SPW) spw = G6_MAX_SPW;
       return (int)spw;
@@ -851,6 +853,16 @@ em_grid_dual_kernel(DevParams p, const unsigned short* __restrict__ col16, RowRe
 inline bool grid_dual_supports_iso(int T) { return T <= G6_MAX_ISO && G6Cfg<8>::fits(T, 1); }
 inline bool grid_dual_possible(int T) { return T <= G6_MAX_ISO && G6Cfg<4>::fits(T, 1); }   // SBQ_GRID_DUAL=1 forces the kernel wherever it can run
 
+// warps per CTA for a locus of T isoforms: a function of the LOCUS alone (the launcher groups loci by it), so that neither the
+// speed nor the summation order of a locus depends on which other loci share its batch
+inline int grid_dual_nc(int T) {
+   static const int force_nc = getenv("SBQ_DUAL_NC") ? atoi(getenv("SBQ_DUAL_NC")) : 0;   // tuning: force the number of warps
+#define SBQ_NC6(NC) if (force_nc ? (force_nc == NC && G6Cfg<NC>::fits(T, 1)) : G6Cfg<NC>::fits(T, 1)) return NC;
+   SBQ_NC6(12) SBQ_NC6(10) SBQ_NC6(8) SBQ_NC6(6) SBQ_NC6(4)
+#undef SBQ_NC6
+   return 0;
+}
+
 struct GridDualBufs {
    void** scratch; size_t* scratch_cap;      // partial / theta copies / counters
    void** col16; size_t* col16_cap;          // u16 slots of the whole batch
@@ -895,7 +907,7 @@ inline int grid_dual_launch_cfg(const DevParams& dp, const int32_t* d_list, int 
 }
 
 // h_rec_off: n_list + 1 record offsets (host; a locus of R rows owns R + 1 records). prepared: the sorted layout of this upload is already in place.
-inline int grid_dual_launch(const DevParams& dp, int64_t nnz_total, const int32_t* d_list, int n_list, int max_iso, const int64_t* h_rec_off,
+inline int grid_dual_launch(const DevParams& dp, int64_t nnz_total, const int32_t* d_list, int n_list, const int* h_iso /* T of every list entry */, const int64_t* h_rec_off,
                             const cudaDeviceProp& prop, const GridDualBufs& bf, bool prepared, cudaStream_t st, int* n_launch) {
    *n_launch = 0;
    if (n_list == 0) return 0;
@@ -938,18 +950,24 @@ inline int grid_dual_launch(const DevParams& dp, int64_t nnz_total, const int32_
          if (h_viol != 0) { fprintf(stderr, "sbq: two-slot layout check failed: %d groups violate it\n", h_viol); return -7; }
       }
    }
-   const char* env_nc = getenv("SBQ_DUAL_NC");   // tuning: force the number of warps
-   const int force_nc = env_nc ? atoi(env_nc) : 0;
-#define SBQ_TRY6(NC, SPW_MIN)                                                                                                             \
-   if (force_nc ? (force_nc == NC && G6Cfg<NC>::fits(max_iso, 1)) : G6Cfg<NC>::fits(max_iso, SPW_MIN))                                    \
-      return grid_dual_launch_cfg<G6Cfg<NC>>(dp, d_list, n_list, max_iso, prop, bf, d_rec_off, d_recs, st, n_launch);
-   SBQ_TRY6(12, 1)
-   SBQ_TRY6(10, 1)
-   SBQ_TRY6(8, 1)
-   SBQ_TRY6(6, 1)
-   SBQ_TRY6(4, 1)
-#undef SBQ_TRY6
-   return -6;
+   // one cooperative launch per run of loci with the same warp count (the planner sorts the list by it)
+   for (int i0 = 0; i0 < n_list;) {
+      const int nc = grid_dual_nc(h_iso[i0]);
+      int i1 = i0, mx = 1;
+      while (i1 < n_list && grid_dual_nc(h_iso[i1]) == nc) { mx = mx > h_iso[i1] ? mx : h_iso[i1]; ++i1; }
+      int rc = -6;
+      switch (nc) {
+         case 12: rc = grid_dual_launch_cfg<G6Cfg<12>>(dp, d_list + i0, i1 - i0, mx, prop, bf, d_rec_off + i0, d_recs, st, n_launch); break;
+         case 10: rc = grid_dual_launch_cfg<G6Cfg<10>>(dp, d_list + i0, i1 - i0, mx, prop, bf, d_rec_off + i0, d_recs, st, n_launch); break;
+         case 8: rc = grid_dual_launch_cfg<G6Cfg<8>>(dp, d_list + i0, i1 - i0, mx, prop, bf, d_rec_off + i0, d_recs, st, n_launch); break;
+         case 6: rc = grid_dual_launch_cfg<G6Cfg<6>>(dp, d_list + i0, i1 - i0, mx, prop, bf, d_rec_off + i0, d_recs, st, n_launch); break;
+         case 4: rc = grid_dual_launch_cfg<G6Cfg<4>>(dp, d_list + i0, i1 - i0, mx, prop, bf, d_rec_off + i0, d_recs, st, n_launch); break;
+         default: break;
+      }
+      if (rc) return rc;
+      i0 = i1;
+   }
+   return 0;
 }
 
 }  // namespace sbq

@@ -102,8 +102,22 @@ __device__ __forceinline__ double iso_fpkm(const DevParams& p, double theta, int
 // the lane-private updates and for the per-column fixed-order sum over lanes).
 // --------------------------------------------------------------------------------------------
 #ifdef SBQ_TRACE
+// -DSBQ_TRACE build: every CTA leaves one record (class, threads, locus, rank, SM, start, end, iterations) in a device array
+// that sbq_debug_trace() copies out - no printf, so the timeline is not distorted (tools/trace_timeline.py).
+constexpr unsigned TRACE_CAP = 1u << 18;
+__device__ unsigned long long g_trace[TRACE_CAP * 4];
+__device__ unsigned g_trace_n;
 __device__ __forceinline__ unsigned long long trace_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ unsigned trace_smid() { unsigned s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); return s; }
+__device__ __forceinline__ void trace_emit(unsigned cs, unsigned nt, int locus, unsigned rank, unsigned long long t0, int iters) {
+   const unsigned i = atomicAdd(&g_trace_n, 1u);
+   if (i < TRACE_CAP) {
+      g_trace[4 * i] = ((unsigned long long)cs << 48) | ((unsigned long long)nt << 32) | (unsigned)locus;
+      g_trace[4 * i + 1] = ((unsigned long long)rank << 48) | ((unsigned long long)trace_smid() << 32) | (unsigned)iters;
+      g_trace[4 * i + 2] = t0;
+      g_trace[4 * i + 3] = trace_now();
+   }
+}
 #endif
 constexpr int WT_WARPS = 8;
 constexpr int WT_MAX_ISO = 32;
@@ -138,7 +152,7 @@ em_warp_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, int ma
       w = __shfl_sync(0xffffffffu, w, 0);
       if (w >= n_list) {
 #ifdef SBQ_TRACE
-         if (threadIdx.x == 0) printf("TRACE warp nt%d locus -1 rank 0 sm %u t0 %llu t1 %llu iters 0\n", WT_WARPS * 32, trace_smid(), trace_t0, trace_now());
+         if (threadIdx.x == 0) trace_emit(0, WT_WARPS * 32, -1, 0, trace_t0, 0);
 #endif
          break;
       }
@@ -1297,7 +1311,7 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
 #endif
    cluster.sync();   // no CTA may exit while a peer can still read its shared memory
 #ifdef SBQ_TRACE
-   if (tid == 0) printf("TRACE c%u nt%d locus %d rank %u sm %u t0 %llu t1 %llu iters %d\n", CS, NT, l, rank, trace_smid(), trace_t0, trace_now(), iters);
+   if (tid == 0) trace_emit(CS, NT, l, rank, trace_t0, iters);
 #endif
 
    if (rank != 0) return;

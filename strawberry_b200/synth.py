@@ -114,6 +114,15 @@ def giant(n_loci=2, rows_per_locus=200_000, seed=4, iso_lo=500, iso_hi=800, mean
                           rows_per_locus=rows_per_locus))
 
 
+def covariates(batch, seed=3):
+    """BASELINE config 3: per-row covariates for the bias-in-EM mode, R x 5 =
+    (gc, gc^2, gc^3, log(bin_len) / 5, mean_frag_len / 1000) with gc ~ Beta(8, 8), bin_len ~ U{50..400}, mean_frag_len ~ N(250, 30)."""
+    rng = np.random.default_rng(seed)
+    R = int(batch["loc_row_off"][-1])
+    gc = rng.beta(8.0, 8.0, R)
+    return np.stack([gc, gc ** 2, gc ** 3, np.log(rng.integers(50, 401, R)) / 5.0, rng.normal(250.0, 30.0, R) / 1000.0], axis=1)
+
+
 DEVICE_GENERATOR_VERSION = "sbq-synth-dev-1"
 _M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
 

@@ -141,6 +141,19 @@ def test_full_size_config2_matches_oracle(q, oracle_mod):
     assert res["stats"]["em_iters_total"] == int(ora["iters"].sum())
 
 
+def test_config5_shape_matches_oracle(oracle_mod):
+    """BASELINE configs[4] shape: the human-shaped generator with 60 000 loci and 100 M fragments,
+    min_iso_frac = 0.01 (the assembly-mode default, so the low-fraction erase path runs) against the oracle: status,
+    iteration count, theta / FPKM / frac / TPM within 1e-6, keep flags equal."""
+    b = synth.human_shaped(n_loci=60000, total_fragments=100_000_000, seed=5)
+    ora = oracle_mod.quantify_batch(b, b["total_mapped_reads"], n_threads=8, min_iso_frac=0.01)
+    res = run_gpu(None, b, min_iso_frac=0.01)
+    assert res["stats"]["n_loci"] == 60000 and int(b["count"].sum()) == 100_000_000
+    worst = assert_matches_oracle(res, ora, b, "configs[4] shape")
+    assert worst < 1e-6
+    assert (res["keep"] == 0).any()
+
+
 def test_full_size_config2_properties(q):
     """BASELINE configs[1] at full size: 20k loci / 10M fragments. Oracle-free, size-independent checks."""
     b = synth.human_shaped()

@@ -21,8 +21,20 @@ else:
     q = api.Quantifier()
 q.submit_flat(b)
 q.upload()
-for _ in range(3):
+L = api.lib()
+for i in range(3):
+    if i == 2 and hasattr(L, "sbq_debug_trace"):      # -DSBQ_TRACE build: drop the records of the warm-up solves
+        import ctypes
+        import numpy as np
+        buf = np.zeros(4 << 18, np.uint64)
+        L.sbq_debug_trace(buf.ctypes.data_as(ctypes.c_void_p), 1 << 18)
     q.solve(b["total_mapped_reads"])
+if hasattr(L, "sbq_debug_trace"):
+    n = L.sbq_debug_trace(buf.ctypes.data_as(ctypes.c_void_p), 1 << 18)
+    for r in buf[:4 * n].reshape(n, 4):
+        cs, nt, locus = int(r[0]) >> 48, (int(r[0]) >> 32) & 0xffff, int(np.int32(np.uint32(int(r[0]) & 0xffffffff)))
+        rank, sm, it = int(r[1]) >> 48, (int(r[1]) >> 32) & 0xffff, int(r[1]) & 0xffffffff
+        print(f"TRACE {'warp' if cs == 0 else 'c%d' % cs} nt{nt} locus {locus} rank {rank} sm {sm} t0 {int(r[2])} t1 {int(r[3])} iters {it}")
 q.finalize_tpm(q.fpkm_sum())
 q.download()
 st = q.stats()
