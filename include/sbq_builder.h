@@ -110,7 +110,9 @@ int  sbq_table_weight_desc(const sbq_table*, sbq_weight_desc* out);
 /* GPU weights (the weight half of the class-table build on the device). The insert model and read
  * length are per context; tables built with defer_weights = 1 are queued like sbq_submit, their alpha is computed by
  * weights_kernel during sbq_upload. A batch is either all deferred or all host-weighted. sbq_fetch_alpha copies the
- * device alpha (nnz doubles, CSR order of the batch) back, e.g. to fill ExonBin::_bin_weight_map for -f output. */
+ * device alpha (nnz doubles, CSR order of the batch) back, e.g. to fill ExonBin::_bin_weight_map for -f output.
+ * Call it BEFORE the first sbq_solve of an upload: the one-off layout pass of the giant-locus tier re-sorts the weights
+ * of giant loci inside each row's CSR range (bank order), after which they no longer line up with the host's columns. */
 int  sbq_set_insert_model(sbq_ctx*, const sbq_insert_model* model, int32_t read_len);
 int  sbq_submit_deferred(sbq_ctx*, const sbq_table* const* tables, int64_t n_tables);
 int  sbq_fetch_alpha(sbq_ctx*, double* alpha);
