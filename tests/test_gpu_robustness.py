@@ -1,0 +1,203 @@
+"""GPU: behaviour at the edges of the C ABI contract - failed submits leave the queue unchanged, borrowed (page-locked) arrays
+are not read after the upload, the asynchronous upload gives the same bits as the synchronous one, wide loci fall to another
+tier instead of failing, and what happens when the stopping rule is met within floating-point noise of the threshold."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from strawberry_b200 import synth
+from util import assert_matches_oracle
+
+pytestmark = pytest.mark.gpu
+KEYS = ("theta", "fpkm", "frac", "tpm", "keep", "iters", "status")
+
+
+def _locus_struct(api, sl, keep):
+    T, rp, col, alpha, count, iso_len = sl
+    arrs = [np.ascontiguousarray(rp, np.int64), np.ascontiguousarray(col, np.int32), np.ascontiguousarray(alpha, np.float64),
+            np.ascontiguousarray(count, np.int32), np.ascontiguousarray(iso_len, np.int32)]
+    keep.append(arrs)
+    return api.Locus(int(T), len(count), *[a.ctypes.data for a in arrs])
+
+
+def test_failed_submit_leaves_the_queue_unchanged(sbq_lib_path):
+    """ADVICE (round 1): a submit that fails validation - or fails half-way - must not leave partial rows in the staging."""
+    from strawberry_b200 import api
+    b = synth.human_shaped(n_loci=40, total_fragments=20_000, seed=61, max_rows=200)
+    good = [synth.locus_slice(b, l) for l in range(40)]
+    q = api.Quantifier()
+    L, keep = api.lib(), []
+    for l in range(20):
+        s = _locus_struct(api, good[l], keep)
+        assert L.sbq_submit(q._h, ctypes.byref(s), 1) == 0
+    # a locus whose row_ptr decreases in the middle: refused, nothing appended
+    T, rp, col, alpha, count, iso_len = good[20]
+    bad_rp = rp.copy()
+    if len(bad_rp) > 3:
+        bad_rp[2] = bad_rp[1] - 1
+    else:
+        bad_rp[-1] = bad_rp[0] - 1
+    s = _locus_struct(api, (T, bad_rp, col, alpha, count, iso_len), keep)
+    assert L.sbq_submit(q._h, ctypes.byref(s), 1) == api.SBQ_ERR_INVALID
+    # a batch of two where the SECOND is bad: the first must not stay queued either
+    s2 = (api.Locus * 2)(_locus_struct(api, good[20], keep), _locus_struct(api, (T, bad_rp, col, alpha, count, iso_len), keep))
+    assert L.sbq_submit(q._h, s2, 2) == api.SBQ_ERR_INVALID
+    with pytest.raises(api.SbqError):           # flat form, same check
+        q.submit_flat(dict(b, row_ptr=np.concatenate([b["row_ptr"][:5], b["row_ptr"][3:4], b["row_ptr"][6:]])))
+    for l in range(20, 40):
+        s = _locus_struct(api, good[l], keep)
+        assert L.sbq_submit(q._h, ctypes.byref(s), 1) == 0
+    q.run(b["total_mapped_reads"])
+    got = q.results()
+    q.close()
+    q2 = api.Quantifier()
+    q2.submit_flat(b)
+    q2.run(b["total_mapped_reads"])
+    ref = q2.results()
+    q2.close()
+    for k in KEYS:
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
+
+
+def test_borrowed_arrays_are_not_read_after_the_upload(sbq_lib_path):
+    """ADVICE (round 1): page-locked arrays used in place may be released once sbq_upload / sbq_run returns - the stats
+    accounting, a second solve and the launch records must not touch them; a re-upload is refused."""
+    from strawberry_b200 import api
+    b = synth.human_shaped(n_loci=1500, total_fragments=700_000, seed=62)
+    frag = np.add.reduceat(b["count"].astype(np.int64), b["loc_row_off"][:-1])
+    p = api.pinned_batch(b)
+    q = api.Quantifier()
+    q.submit_flat(p)
+    q.upload()
+    for k in ("loc_row_off", "loc_iso_off", "row_ptr", "col", "count", "iso_len"):   # "free" them: poison the caller's arrays
+        p[k][...] = -7
+    p["alpha"][...] = np.nan
+    q.solve(b["total_mapped_reads"])
+    q.finalize_tpm(q.fpkm_sum())
+    q.download()
+    res, st, launches = q.results(), q.stats(), q.launch_stats()
+    assert st["frag_iters"] == int((frag * res["iters"]).sum())
+    assert sum(l["nnz"] for l in launches) == int(b["row_ptr"][-1])
+    q.set_plan(2, 1)
+    with pytest.raises(api.SbqError) as e:      # nothing to upload from any more
+        q.upload()
+    assert e.value.code == api.SBQ_ERR_STATE
+    q.close()
+    q2 = api.Quantifier()
+    q2.submit_flat(b)
+    q2.run(b["total_mapped_reads"])
+    ref = q2.results()
+    q2.close()
+    for k in KEYS:
+        assert np.array_equal(res[k], ref[k], equal_nan=True), k
+
+
+def test_asynchronous_upload_gives_the_same_bits(sbq_lib_path):
+    from strawberry_b200 import api
+    b = synth.concat([synth.human_shaped(n_loci=3000, total_fragments=1_500_000, seed=63), synth.giant(n_loci=1, rows_per_locus=20_000, seed=4)])
+    p = api.pinned_batch(b)
+    q = api.Quantifier()
+    q.submit_flat(p)
+    q.upload()                      # synchronous
+    q.solve(b["total_mapped_reads"])
+    q.finalize_tpm(q.fpkm_sum())
+    q.download()
+    sync = q.results()
+    for _ in range(2):
+        q.clear()
+        q.submit_flat(p)
+        q.upload_begin()            # copies in priority order, launches wait for their own data
+        q.solve(b["total_mapped_reads"])
+        q.finalize_tpm(q.fpkm_sum())
+        q.download()
+        got = q.results()
+        for k in KEYS:
+            assert np.array_equal(got[k], sync[k], equal_nan=True), k
+        assert q.stats()["upload_ms"] > 0
+    q.clear()                       # a clear right after an asynchronous upload waits for its copies
+    q.submit_flat(p)
+    q.upload_begin()
+    q.clear()
+    q.close()
+
+
+def test_wide_loci_fall_to_another_tier(sbq_lib_path, oracle_mod):
+    """VERDICT (round 1): a medium locus too wide for the cluster tier's resident layout must not fail the upload. T = 3600 is
+    SBQ_MAX_ISO, the width every multi-row tier supports; T = 3601 is refused at submit time."""
+    from strawberry_b200 import api
+    rng = np.random.default_rng(64)
+
+    def wide(T, R, k):
+        cols = [np.sort(rng.choice(T, k, replace=False)) for _ in range(R)]
+        rp = np.arange(R + 1, dtype=np.int64) * k
+        return dict(loc_row_off=np.array([0, R], np.int64), loc_iso_off=np.array([0, T], np.int64), row_ptr=rp,
+                    col=np.concatenate(cols).astype(np.int32), alpha=10.0 ** rng.uniform(-4, -1.5, R * k), count=rng.integers(0, 9, R).astype(np.int32),
+                    iso_len=rng.integers(400, 8000, T).astype(np.int32), total_mapped_reads=1_000_000, meta={})
+    b = synth.concat([wide(3600, 400, 30), wide(2000, 900, 12), wide(3000, 3000, 40)])
+    ora = oracle_mod.quantify_batch(b, b["total_mapped_reads"], max_iter=60)
+    for tier in (0, 2, 3):
+        q = api.Quantifier(max_iter=60)
+        q.set_plan(tier, 0)
+        q.submit_flat(b)
+        q.run(b["total_mapped_reads"])
+        res = q.results()
+        q.close()
+        assert_matches_oracle(res, ora, b, f"wide loci, tier {tier}")
+    q = api.Quantifier()
+    with pytest.raises(api.SbqError) as e:
+        q.submit_flat(wide(3601, 10, 3))
+    assert e.value.code == api.SBQ_ERR_UNSUPPORTED
+    q.close()
+
+
+def test_stopping_rule_within_floating_point_noise_of_the_threshold(sbq_lib_path, oracle_mod):
+    """The reference stops when ||theta' - theta||_2 < 1e-2 and returns the PREVIOUS iterate (src/estimate.cpp:479-480), so a
+    threshold met within rounding noise decides whether one more E-step runs. The kernels sum in a different order than Eigen
+    (and than the oracle), so exact agreement of the iteration count cannot be guaranteed there. This test pins what IS
+    guaranteed: (1) with the threshold a relative 1e-9 away from the norm of iteration k - a margin six orders of magnitude
+    above the rounding noise of the norm - every tier stops exactly where the oracle does; (2) with the threshold set to the
+    oracle's own norm of iteration k, bit for bit (the worst case), the iteration count differs by at most one and theta by
+    at most one EM step, i.e. by less than the threshold in the 2-norm."""
+    from strawberry_b200 import api
+    rng = np.random.default_rng(65)
+    T, R = 9, 140
+    model = rng.random((R, T)) * (rng.random((R, T)) < 0.45) * 0.02
+    model[model.sum(1) == 0, 0] = 0.01
+    count = rng.integers(0, 400, R).astype(np.int32)
+    # plain numpy restatement of the EM to read the norms of the change per iteration
+    th = np.full(T, count.sum() / T)
+    F = model.copy()
+    norms = []
+    for it in range(60):
+        d = F @ th
+        new = ((count[:, None] * F * th[None, :]) / d[:, None]).sum(0)
+        s = F.sum(0)
+        F = np.where(s[None, :] != 0, F / np.where(s == 0, 1, s)[None, :], F)
+        norms.append(float(np.linalg.norm(new - th)))
+        th = new
+    k = next(i for i, n in enumerate(norms) if n < 0.5 and i >= 5)      # a step well inside the run, change of a fraction of a read
+    rows, cols = np.nonzero(model)
+    rp = np.zeros(R + 1, np.int64)
+    np.cumsum(np.bincount(rows, minlength=R), out=rp[1:])
+    b = dict(loc_row_off=np.array([0, R], np.int64), loc_iso_off=np.array([0, T], np.int64), row_ptr=rp, col=cols.astype(np.int32),
+             alpha=model[rows, cols], count=count, iso_len=np.full(T, 1500, np.int32), total_mapped_reads=int(count.sum()), meta={})
+
+    def solve(tol, tier):
+        q = api.Quantifier(theta_tol=tol)
+        q.set_plan(tier, 1 if tier == 2 else 0)
+        q.submit_flat(b)
+        q.run(b["total_mapped_reads"])
+        r = q.results()
+        q.close()
+        return int(r["iters"][0]), r["theta"]
+    for tier in (1, 2, 3):
+        for rel, expect in ((1 + 1e-9, k + 1), (1 - 1e-9, k + 2)):      # just above the norm: stop at E-step k + 1; just below: one more
+            st, th_o, it_o = oracle_mod.em_csr(T, rp, cols, model[rows, cols], count, theta_tol=norms[k] * rel)
+            it_g, th_g = solve(norms[k] * rel, tier)
+            assert it_o == expect and it_g == expect, (tier, rel, it_o, it_g)
+            assert np.allclose(th_g, th_o, rtol=1e-9)
+        st, th_o, it_o = oracle_mod.em_csr(T, rp, cols, model[rows, cols], count, theta_tol=norms[k])
+        it_g, th_g = solve(norms[k], tier)
+        assert abs(it_g - it_o) <= 1, (tier, it_g, it_o)
+        assert np.linalg.norm(th_g - th_o) <= norms[k] * (1 + 1e-9)
