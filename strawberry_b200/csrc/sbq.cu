@@ -176,7 +176,7 @@ struct sbq_ctx {
    size_t warp_list_off = 0, grid_list_off = 0;
 
    // device
-   DevBuf d_in, d_out, d_lists, d_grid_scratch, d_col16, d_rowrec, d_csc, d_synth;
+   DevBuf d_in, d_out, d_lists, d_grid_scratch, d_col16, d_rowrec, d_csc, d_synth, d_pk;
    bool col16_ready = false, grid_tma_ok = false, grid_dual_ok = false;
    std::vector<int64_t> grid_rec_off;            // row-record offset of every two-slot-kernel locus (+ total), list order
    size_t grid_n_dual = 0;                       // the first grid_n_dual entries of grid_list run on the two-slot kernel, the rest on the TMA ring / register-staged kernel
@@ -684,7 +684,7 @@ void sbq_destroy(sbq_ctx* c) {
    c->h_lists.release();
    c->r_theta.release(); c->r_fpkm.release(); c->r_frac.release(); c->r_tpm.release();
    c->r_locus_fpkm.release(); c->r_keep.release(); c->r_iters.release(); c->r_status.release(); c->r_frags.release(); c->d_frags.release();
-   c->d_in.release(); c->d_out.release(); c->d_lists.release(); c->d_grid_scratch.release(); c->d_col16.release(); c->d_rowrec.release(); c->d_csc.release(); c->d_synth.release(); c->d_bias.release();
+   c->d_in.release(); c->d_out.release(); c->d_lists.release(); c->d_grid_scratch.release(); c->d_col16.release(); c->d_rowrec.release(); c->d_csc.release(); c->d_synth.release(); c->d_pk.release(); c->d_bias.release();
    c->h_cov.release(); c->r_beta.release(); c->r_outer.release();
    c->h_wseg.release(); c->h_wn.release(); c->h_wmask.release(); c->h_wpool.release(); c->h_wlen.release(); c->h_wpool_off.release(); c->d_weights.release();
    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -1067,7 +1067,7 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
       const int32_t* d_grid = c->d_lists_p + c->grid_list_off;
       const int n_dual = (int)c->grid_n_dual, n_rest = (int)c->grid_list.size() - n_dual;
       if (n_dual) {
-         GridDualBufs bf{&c->d_grid_scratch.p, &c->d_grid_scratch.cap, &c->d_col16.p, &c->d_col16.cap, &c->d_rowrec.p, &c->d_rowrec.cap};
+         GridDualBufs bf{&c->d_grid_scratch.p, &c->d_grid_scratch.cap, &c->d_col16.p, &c->d_col16.cap, &c->d_rowrec.p, &c->d_rowrec.cap, &c->d_pk.p, &c->d_pk.cap};
          int nl = 0;
          std::vector<int> h_iso((size_t)n_dual);
          for (int i = 0; i < n_dual; ++i) h_iso[i] = c->meta[c->grid_list[i]].T;

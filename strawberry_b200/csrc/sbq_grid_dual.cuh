@@ -56,6 +56,18 @@ constexpr int G6_MAX_SPW = 4;                    // ring stages per warp (at mos
 constexpr int G6_MAX_WARPS = 16;
 constexpr int G6_MAX_ISO = 4048;                 // slot * 8 must fit the u16 stream: (2 Tp + 64) * 8 <= 65535
 
+// Packed chunk stream (written once per upload by dual_pack_kernel): everything a warp turn needs - the chunk's 8 + 1 row records,
+// its weights and its u16 slots - lies back to back at a fixed stride, so a stage is refilled by ONE bulk copy instead of three
+// (issuing the three copies plus the proxy fence took ~590 of the ~3 650 cycles of a turn on the thread that issues them).
+//   chunk g of a locus:  [ 9 records, 144 B | alpha, n x 8 B rounded up to 16 B | slots, n x 2 B rounded up to 16 B ]   at g * G6_PK_STRIDE
+// A chunk with more than G6_PK_CAP non-zeros only carries its records (its rows are walked from the CSR arrays).
+constexpr int G6_PK_ROWS = 2 * G6_NR;                                    // rows per chunk
+constexpr int G6_PK_CAP = G6_PK_ROWS * 56;                               // non-zeros a staged chunk holds at most
+constexpr int G6_PK_RECS = (G6_PK_ROWS + 1) * (int)sizeof(RowRec);       // 144 B
+constexpr int G6_PK_STRIDE = ((G6_PK_RECS + ((G6_PK_CAP + 1) & ~1) * 8 + ((G6_PK_CAP + 7) & ~7) * 2 + 127) / 128) * 128;   // 4 736 B
+__host__ __device__ __forceinline__ unsigned g6_pk_abytes(unsigned n) { return ((n + 1u) & ~1u) * 8u; }
+__host__ __device__ __forceinline__ unsigned g6_pk_cbytes(unsigned n) { return ((n + 7u) & ~7u) * 2u; }
+
 __host__ __device__ __forceinline__ int g6_tp(int T) { return (T + 15) & ~15; }
 __host__ __device__ __forceinline__ int g6_slot_b(int j, int Tp) { return Tp + (j & ~15) + ((j + (j >> 4)) & 15); }
 
@@ -68,15 +80,14 @@ template <int NC>
 struct G6Cfg {
    static constexpr int CONSUMERS = NC;
    static constexpr int NT = NC * 32;
-   static constexpr int CROWS = 2 * G6_NR;                // rows per chunk (four per half-warp)
-   static constexpr int CAP = CROWS * 56;                 // non-zeros a stage holds; fuller chunks are read from global memory
-   // stage layout (bytes): alpha | col16 | records
-   static constexpr int A_BYTES = (CAP + 2 + 16) * 8;     // + slack: lanes past a step's last entry still read (and discard) 8 bytes
-   static constexpr int C_OFF = A_BYTES;
-   static constexpr int C_BYTES = (((CAP + 8 + 16) * 2 + 15) / 16) * 16;
-   static constexpr int R_OFF = C_OFF + C_BYTES;
-   static constexpr int R_BYTES = (CROWS + 1) * (int)sizeof(RowRec);   // + the record after the chunk (its offset ends the chunk)
-   static constexpr int STAGE_BYTES = ((R_OFF + R_BYTES + 127) / 128) * 128;
+   static constexpr int CROWS = G6_PK_ROWS;               // rows per chunk (four per half-warp)
+   static constexpr int CAP = G6_PK_CAP;                  // non-zeros a stage holds; fuller chunks are read from global memory
+   // stage layout (bytes) = the packed chunk: records | alpha | slots. Lanes past a step's last entry still read (and discard)
+   // up to 18 weights and 16 slots behind the chunk's own: the stage leaves room for that (those bytes are older weights or
+   // slots - finite as doubles for every T this kernel takes - never NaN, so "alpha x theta[dummy] = 0" holds).
+   static constexpr int A_OFF = G6_PK_RECS;
+   static constexpr int STAGE_BYTES = G6_PK_STRIDE;
+   static_assert(G6_PK_RECS + ((G6_PK_CAP + 1) & ~1) * 8 + (G6_PK_CAP + 16 + 8) * 2 <= STAGE_BYTES, "room for the slot over-read behind the fullest chunk");
    static size_t fixed_bytes(int T) { return (size_t)(2 * g6_tp(T) + 64) * (1 + NC) * sizeof(double); }   // th2[2Tp+64] | acc[NC][2Tp+64]
    static int stages_per_warp(int T) {   // ring depth per warp that fits beside the accumulators
       // 227 KB usable per CTA (232 448 B) minus the kernel's static shared memory (640 B) and a little slack: T = 800 still gets
@@ -344,6 +355,40 @@ dual_verify_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, co
    }
 }
 
+// One warp per chunk: copy the chunk's records, weights and slots (all final after dual_prepare_kernel) into the packed stream.
+__global__ void __launch_bounds__(256)
+dual_pack_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, const int64_t* __restrict__ rec_off, const RowRec* __restrict__ recs,
+                 const unsigned short* __restrict__ col16, const int64_t* __restrict__ pk_off, unsigned char* __restrict__ pk) {
+   const int lane = threadIdx.x & 31;
+   const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+   for (int item = 0; item < n_list; ++item) {
+      const int l = list[item];
+      const int64_t r0 = p.loc_row_off[l];
+      const int64_t R = p.loc_row_off[l + 1] - r0;
+      const int64_t kbase = p.row_ptr[r0];
+      const RowRec* rec_l = recs + rec_off[item];
+      const int64_t n_chunk = (R + G6_PK_ROWS - 1) / G6_PK_ROWS;
+      for (int64_t g = wid; g < n_chunk; g += nw) {
+         const int64_t i0 = g * G6_PK_ROWS, i1 = min(i0 + (int64_t)G6_PK_ROWS, R);
+         unsigned char* dst = pk + (size_t)(pk_off[item] + g) * G6_PK_STRIDE;
+         const uint32_t ck0 = rec_l[i0].koff, ck1 = rec_l[i1].koff;
+         if (lane <= G6_PK_ROWS) {
+            uint4 v = make_uint4(0u, 0u, 0xffffffffu, ck1);      // rows the chunk does not have: no entries, dropped, offset = end
+            if (i0 + lane <= i1) v = *reinterpret_cast<const uint4*>(rec_l + i0 + lane);
+            *reinterpret_cast<uint4*>(dst + lane * 16) = v;
+         }
+         const unsigned n = ck1 - ck0;
+         if (n <= (unsigned)G6_PK_CAP) {
+            double* da = reinterpret_cast<double*>(dst + G6_PK_RECS);
+            unsigned short* dc = reinterpret_cast<unsigned short*>(dst + G6_PK_RECS + g6_pk_abytes(n));
+            const int64_t k0 = kbase + ck0;
+            for (unsigned x = lane; x < ((n + 1u) & ~1u); x += 32) da[x] = x < n ? p.alpha[k0 + x] : 0.0;
+            for (unsigned x = lane; x < ((n + 7u) & ~7u); x += 32) dc[x] = x < n ? col16[k0 + x] : (unsigned short)0;
+         }
+      }
+   }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // consumer side
 // ------------------------------------------------------------------------------------------------------------------
@@ -559,26 +604,20 @@ __device__ __forceinline__ unsigned g6_turn(const DevParams& p, const double* __
    return flagged;
 }
 
-// Lane 0: start the three bulk copies of CTA-local chunk c into stage `st` (k0, k1: its non-zero range, absolute).
+// Lane 0: start the bulk copy of CTA-local chunk c of the packed stream into stage `st` (k0, k1: its non-zero range).
 template <typename C>
-__device__ __forceinline__ void g6_issue(const DevParams& p, const unsigned short* __restrict__ col16, const RowRec* __restrict__ rec_cta, int n_rows, int c,
-                                         int64_t k0, int64_t k1, char* st, uint64_t* full) {
-   const bool staged = k1 - k0 <= (int64_t)C::CAP;   // a fuller chunk only brings its records
-   const int64_t ka = k0 & ~(int64_t)1, kc = k0 & ~(int64_t)7;
-   const unsigned a_bytes = staged ? (unsigned)(((k1 - ka + 1) & ~(int64_t)1) * 8) : 0u;
-   const unsigned c_bytes = staged ? (unsigned)(((k1 - kc + 7) & ~(int64_t)7) * 2) : 0u;
-   const int i0 = c * C::CROWS, i1 = min(i0 + C::CROWS, n_rows);
-   const unsigned r_bytes = (unsigned)((i1 - i0 + 1) * sizeof(RowRec));
+__device__ __forceinline__ void g6_issue(const unsigned char* __restrict__ pk_cta, int c, int64_t k0, int64_t k1, char* st, uint64_t* full) {
+   const unsigned n = (unsigned)(k1 - k0);
+   const unsigned bytes = (unsigned)G6_PK_RECS + (n <= (unsigned)C::CAP ? g6_pk_abytes(n) + g6_pk_cbytes(n) : 0u);   // a fuller chunk only brings its records
    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stage was last read with ordinary shared-memory loads
-   mbar_expect_tx(full, a_bytes + c_bytes + r_bytes);
-   if (a_bytes) bulk_g2s(st, p.alpha + ka, a_bytes, full);
-   if (c_bytes) bulk_g2s(st + C::C_OFF, col16 + kc, c_bytes, full);
-   bulk_g2s(st + C::R_OFF, rec_cta + i0, r_bytes, full);
+   mbar_expect_tx(full, bytes);
+   bulk_g2s(st, pk_cta + (size_t)c * G6_PK_STRIDE, bytes, full);
 }
 
 // One pass of this warp over its chunks (w, w + NC, ...) of the CTA's rows.
 template <typename C, bool SETUP>
-__device__ __forceinline__ void g6_pass(const DevParams& p, const unsigned short* __restrict__ col16, RowRec* __restrict__ rec_cta /* row 0 of this CTA */,
+__device__ __forceinline__ void g6_pass(const DevParams& p, const unsigned short* __restrict__ col16, unsigned char* __restrict__ pk_cta /* packed chunk 0 of this CTA */,
+                                        RowRec* __restrict__ rec_cta /* row 0 of this CTA in the record array (rows walked from the CSR arrays) */,
                                         const int64_t* __restrict__ rp_cta /* row pointer of the CTA's row 0 */, const int64_t kbase /* first non-zero of the locus */,
                                         int64_t row_abs0 /* absolute row of the CTA's row 0 */, int n_rows, int n_chunk, G6Ring& ring,
                                         int dummy0 /* byte offset of the first dummy slot = 8 * 2 Tp */, const double* th2, double* my, long long& tot, long long& kept, int& zero) {
@@ -590,7 +629,7 @@ __device__ __forceinline__ void g6_pass(const DevParams& p, const unsigned short
       int sx = ring.next;
       for (int i = 0; i < min(ring.spw, n_mine); ++i) {
          const int c = warp + i * C::CONSUMERS;
-         g6_issue<C>(p, col16, rec_cta, n_rows, c, rp_cta[min(c * C::CROWS, n_rows)], rp_cta[min((c + 1) * C::CROWS, n_rows)],
+         g6_issue<C>(pk_cta, c, rp_cta[min(c * C::CROWS, n_rows)], rp_cta[min((c + 1) * C::CROWS, n_rows)],
                      ring.stage + (size_t)sx * C::STAGE_BYTES, &ring.full[sx]);
          sx = sx + 1 == ring.spw ? 0 : sx + 1;
       }
@@ -614,19 +653,20 @@ __device__ __forceinline__ void g6_pass(const DevParams& p, const unsigned short
       ring.phase ^= 1u << sidx;
       ring.next = sidx + 1 == ring.spw ? 0 : sidx + 1;
       char* st = ring.stage + (size_t)sidx * C::STAGE_BYTES;
-      const RowRec* rec_s = (const RowRec*)(st + C::R_OFF);
+      const RowRec* rec_s = (const RowRec*)st;
       const uint32_t ck0 = rec_s[0].koff;
       const uint32_t ck1 = rec_s[i1 - i0].koff;
       const bool staged = ck1 - ck0 <= (uint32_t)C::CAP;   // same decision as g6_issue
       const int h0 = i0 + (lane >> 4) * G6_NR;             // first row of this half-warp
       unsigned walk = 0;                                   // bit i: row i0 + i is walked from global memory
       auto refill = [&]() {
-         if (lane == 0 && cn < n_chunk) g6_issue<C>(p, col16, rec_cta, n_rows, cn, kn0, kn1, st, &ring.full[sidx]);
+         if (lane == 0 && cn < n_chunk) g6_issue<C>(pk_cta, cn, kn0, kn1, st, &ring.full[sidx]);
       };
       if (staged) {
-         const int64_t k0 = kbase + ck0;
-         const unsigned fl = g6_turn<SETUP>(p, (const double*)st + (k0 & 1), (const unsigned short*)(st + C::C_OFF) + (k0 & 7), rec_s + (min(h0, i1 - 1) - i0),
-                                            rec_cta + h0, p.count + row_abs0 + h0, p.neff + row_abs0 + h0, max(0, min(G6_NR, i1 - h0)), i1 - i0 == C::CROWS, ck0, dummy0, th2, my,
+         // setup pass: the effective counts go into the PACKED records (what the EM passes stage); walked rows keep theirs in the record array
+         RowRec* rec_pk = reinterpret_cast<RowRec*>(pk_cta + (size_t)c * G6_PK_STRIDE) + (h0 - i0);
+         const unsigned fl = g6_turn<SETUP>(p, (const double*)(st + C::A_OFF), (const unsigned short*)(st + C::A_OFF + g6_pk_abytes(ck1 - ck0)), rec_s + (min(h0, i1 - 1) - i0),
+                                            rec_pk, p.count + row_abs0 + h0, p.neff + row_abs0 + h0, max(0, min(G6_NR, i1 - h0)), i1 - i0 == C::CROWS, ck0, dummy0, th2, my,
                                             tot, kept, zero, refill, g6_t_);
          walk = __shfl_sync(0xffffffffu, fl, 0) | (__shfl_sync(0xffffffffu, fl, 16) << G6_NR);
       } else {
@@ -648,7 +688,8 @@ __device__ __forceinline__ void g6_pass(const DevParams& p, const unsigned short
 template <typename C>
 __global__ void __launch_bounds__(C::NT, 1)
 em_grid_dual_kernel(DevParams p, const unsigned short* __restrict__ col16, RowRec* __restrict__ recs, const int64_t* __restrict__ rec_off,
-                    const int32_t* __restrict__ list, int n_list, GridScratch gs, double* cur_glob /* [n_cta][tstride] */, int spw) {
+                    const int32_t* __restrict__ list, int n_list, GridScratch gs, double* cur_glob /* [n_cta][tstride] */, int spw,
+                    unsigned char* __restrict__ pk, const int64_t* __restrict__ pk_off) {
    cg::grid_group grid = cg::this_grid();
    extern __shared__ __align__(128) unsigned char g6_smem[];
    __shared__ double red[C::NT / 32];
@@ -706,6 +747,7 @@ em_grid_dual_kernel(DevParams p, const unsigned short* __restrict__ col16, RowRe
       const int n_chunk = (rb - ra + C::CROWS - 1) / C::CROWS;
       const int64_t kbase = rp[0];
       RowRec* rec_cta = rec_l + ra;
+      unsigned char* pk_cta = pk + (size_t)(pk_off[item] + ra / C::CROWS) * G6_PK_STRIDE;   // ra is a multiple of the chunk size
       double* my_acc = acc + (size_t)warp * T2;
       // sum of a column's two slots over the warp-private accumulators (fixed order), accumulators cleared
       auto fold = [&](int j) {
@@ -723,7 +765,7 @@ em_grid_dual_kernel(DevParams p, const unsigned short* __restrict__ col16, RowRe
       // ---- setup pass
       long long tot = 0, kept = 0;
       int zero = 0;
-      g6_pass<C, true>(p, col16, rec_cta, rp + ra, kbase, r0 + ra, rb - ra, n_chunk, ring, 16 * Tp, th2, my_acc, tot, kept, zero);
+      g6_pass<C, true>(p, col16, pk_cta, rec_cta, rp + ra, kbase, r0 + ra, rb - ra, n_chunk, ring, 16 * Tp, th2, my_acc, tot, kept, zero);
       tot = warp_sum_ll(tot);
       kept = warp_sum_ll(kept);
       if (lane == 0 && (tot | kept)) {
@@ -763,7 +805,7 @@ em_grid_dual_kernel(DevParams p, const unsigned short* __restrict__ col16, RowRe
             iters = it + 1;
             zero = 0;
             long long d0 = 0, d1 = 0;
-            g6_pass<C, false>(p, col16, rec_cta, rp + ra, kbase, r0 + ra, rb - ra, n_chunk, ring, 16 * Tp, th2, my_acc, d0, d1, zero);
+            g6_pass<C, false>(p, col16, pk_cta, rec_cta, rp + ra, kbase, r0 + ra, rb - ra, n_chunk, ring, 16 * Tp, th2, my_acc, d0, d1, zero);
             zero = __syncthreads_or(zero);
             if (zero && tid == 0) atomicOr(&gs.zero_flag[item], 1);
             for (int j = tid; j < T; j += C::NT) my_partial[j] = fold(j);
@@ -858,6 +900,7 @@ inline bool grid_dual_possible(int T) { return T <= G6_MAX_ISO && G6Cfg<4>::fits
 inline int grid_dual_nc(int T) {
    static const int force_nc = getenv("SBQ_DUAL_NC") ? atoi(getenv("SBQ_DUAL_NC")) : 0;   // tuning: force the number of warps
 #define SBQ_NC6(NC) if (force_nc ? (force_nc == NC && G6Cfg<NC>::fits(T, 1)) : G6Cfg<NC>::fits(T, 1)) return NC;
+   // (14 warps fit up to T = 624 but force 128 registers per thread: measured 0.1427 ms per pass against 0.1433 with 12 - not worth a variant)
    SBQ_NC6(12) SBQ_NC6(10) SBQ_NC6(8) SBQ_NC6(6) SBQ_NC6(4)
 #undef SBQ_NC6
    return 0;
@@ -866,12 +909,13 @@ inline int grid_dual_nc(int T) {
 struct GridDualBufs {
    void** scratch; size_t* scratch_cap;      // partial / theta copies / counters
    void** col16; size_t* col16_cap;          // u16 slots of the whole batch
-   void** recs; size_t* recs_cap;            // per-locus record offsets (int64, at the front) + row records of the giant loci
+   void** recs; size_t* recs_cap;            // per-locus record offsets and first packed chunks (int64 each, at the front) + row records of the giant loci
+   void** pk; size_t* pk_cap;                // packed chunk stream of the giant loci (G6_PK_STRIDE bytes per 8-row chunk)
 };
 
 template <typename C>
 inline int grid_dual_launch_cfg(const DevParams& dp, const int32_t* d_list, int n_list, int max_iso, const cudaDeviceProp& prop, const GridDualBufs& bf,
-                                const int64_t* d_rec_off, RowRec* d_recs, cudaStream_t st, int* n_launch) {
+                                const int64_t* d_rec_off, RowRec* d_recs, const int64_t* d_pk_off, cudaStream_t st, int* n_launch) {
    const int spw = C::stages_per_warp(max_iso);
    const size_t smem = (size_t)spw * C::CONSUMERS * C::STAGE_BYTES + C::fixed_bytes(max_iso);
    auto kernel = em_grid_dual_kernel<C>;
@@ -900,7 +944,9 @@ inline int grid_dual_launch_cfg(const DevParams& dp, const int32_t* d_list, int 
    DevParams dpc = dp;
    const unsigned short* c16 = (const unsigned short*)*bf.col16;
    int ns_arg = spw;
-   void* args[] = {(void*)&dpc, (void*)&c16, (void*)&d_recs, (void*)&d_rec_off, (void*)&d_list, (void*)&n_list, (void*)&gs, (void*)&cur_glob, (void*)&ns_arg};
+   unsigned char* pk = (unsigned char*)*bf.pk;
+   void* args[] = {(void*)&dpc, (void*)&c16, (void*)&d_recs, (void*)&d_rec_off, (void*)&d_list, (void*)&n_list, (void*)&gs, (void*)&cur_glob, (void*)&ns_arg,
+                   (void*)&pk, (void*)&d_pk_off};
    if (cudaLaunchCooperativeKernel((void*)kernel, dim3(nb), dim3(C::NT), args, smem, st) != cudaSuccess) return -3;
    ++*n_launch;
    return 0;
@@ -920,8 +966,24 @@ inline int grid_dual_launch(const DevParams& dp, int64_t nnz_total, const int32_
       *bf.col16_cap = need16;
       prepared = false;
    }
-   const size_t off_bytes = (((size_t)(n_list + 1) * sizeof(int64_t) + 255) / 256) * 256;
+   const size_t off_bytes = (((size_t)(n_list + 1) * 2 * sizeof(int64_t) + 255) / 256) * 256;   // record offsets | first packed chunks
    const size_t need_rec = off_bytes + (size_t)(h_rec_off[n_list] + 64) * sizeof(RowRec);
+   std::vector<int64_t> h_off(2 * (size_t)(n_list + 1));
+   for (int i = 0; i <= n_list; ++i) h_off[i] = h_rec_off[i];
+   h_off[n_list + 1] = 0;
+   for (int i = 0; i < n_list; ++i) {
+      const int64_t R = h_rec_off[i + 1] - h_rec_off[i] - 1;   // a locus of R rows owns R + 1 records
+      h_off[n_list + 1 + i + 1] = h_off[n_list + 1 + i] + (R + G6_PK_ROWS - 1) / G6_PK_ROWS;
+   }
+   const size_t need_pk = (size_t)h_off[2 * n_list + 1] * G6_PK_STRIDE + 256;
+   if (need_pk > *bf.pk_cap) {
+      if (*bf.pk) cudaFree(*bf.pk);
+      *bf.pk = nullptr;
+      *bf.pk_cap = 0;
+      if (cudaMalloc(bf.pk, need_pk) != cudaSuccess) return -4;
+      *bf.pk_cap = need_pk;
+      prepared = false;
+   }
    if (need_rec > *bf.recs_cap) {
       if (*bf.recs) cudaFree(*bf.recs);
       *bf.recs = nullptr;
@@ -931,9 +993,11 @@ inline int grid_dual_launch(const DevParams& dp, int64_t nnz_total, const int32_
       prepared = false;
    }
    const int64_t* d_rec_off = (const int64_t*)*bf.recs;
+   const int64_t* d_pk_off = d_rec_off + (n_list + 1);
    RowRec* d_recs = (RowRec*)((char*)*bf.recs + off_bytes);
    if (!prepared) {
-      if (cudaMemcpyAsync(*bf.recs, h_rec_off, (size_t)(n_list + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st) != cudaSuccess) return -3;
+      // (pageable host vector: the copy is staged by the runtime before the call returns)
+      if (cudaMemcpyAsync(*bf.recs, h_off.data(), h_off.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st) != cudaSuccess) return -3;
       const size_t psmem = (size_t)G6_PREP_WARPS * sizeof(G6PrepTile);
       if (cudaFuncSetAttribute(dual_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem) != cudaSuccess) return -3;
       dual_prepare_kernel<<<prop.multiProcessorCount * 2, G6_PREP_WARPS * 32, psmem, st>>>(dp, d_list, n_list, d_rec_off, d_recs, (unsigned short*)*bf.col16);
@@ -949,6 +1013,9 @@ inline int grid_dual_launch(const DevParams& dp, int64_t nnz_total, const int32_
          cudaFree(d_viol);
          if (h_viol != 0) { fprintf(stderr, "sbq: two-slot layout check failed: %d groups violate it\n", h_viol); return -7; }
       }
+      dual_pack_kernel<<<prop.multiProcessorCount * 8, 256, 0, st>>>(dp, d_list, n_list, d_rec_off, d_recs, (const unsigned short*)*bf.col16, d_pk_off,
+                                                                   (unsigned char*)*bf.pk);
+      ++*n_launch;
    }
    // one cooperative launch per run of loci with the same warp count (the planner sorts the list by it)
    for (int i0 = 0; i0 < n_list;) {
@@ -957,11 +1024,11 @@ inline int grid_dual_launch(const DevParams& dp, int64_t nnz_total, const int32_
       while (i1 < n_list && grid_dual_nc(h_iso[i1]) == nc) { mx = mx > h_iso[i1] ? mx : h_iso[i1]; ++i1; }
       int rc = -6;
       switch (nc) {
-         case 12: rc = grid_dual_launch_cfg<G6Cfg<12>>(dp, d_list + i0, i1 - i0, mx, prop, bf, d_rec_off + i0, d_recs, st, n_launch); break;
-         case 10: rc = grid_dual_launch_cfg<G6Cfg<10>>(dp, d_list + i0, i1 - i0, mx, prop, bf, d_rec_off + i0, d_recs, st, n_launch); break;
-         case 8: rc = grid_dual_launch_cfg<G6Cfg<8>>(dp, d_list + i0, i1 - i0, mx, prop, bf, d_rec_off + i0, d_recs, st, n_launch); break;
-         case 6: rc = grid_dual_launch_cfg<G6Cfg<6>>(dp, d_list + i0, i1 - i0, mx, prop, bf, d_rec_off + i0, d_recs, st, n_launch); break;
-         case 4: rc = grid_dual_launch_cfg<G6Cfg<4>>(dp, d_list + i0, i1 - i0, mx, prop, bf, d_rec_off + i0, d_recs, st, n_launch); break;
+         case 12: rc = grid_dual_launch_cfg<G6Cfg<12>>(dp, d_list + i0, i1 - i0, mx, prop, bf, d_rec_off + i0, d_recs, d_pk_off + i0, st, n_launch); break;
+         case 10: rc = grid_dual_launch_cfg<G6Cfg<10>>(dp, d_list + i0, i1 - i0, mx, prop, bf, d_rec_off + i0, d_recs, d_pk_off + i0, st, n_launch); break;
+         case 8: rc = grid_dual_launch_cfg<G6Cfg<8>>(dp, d_list + i0, i1 - i0, mx, prop, bf, d_rec_off + i0, d_recs, d_pk_off + i0, st, n_launch); break;
+         case 6: rc = grid_dual_launch_cfg<G6Cfg<6>>(dp, d_list + i0, i1 - i0, mx, prop, bf, d_rec_off + i0, d_recs, d_pk_off + i0, st, n_launch); break;
+         case 4: rc = grid_dual_launch_cfg<G6Cfg<4>>(dp, d_list + i0, i1 - i0, mx, prop, bf, d_rec_off + i0, d_recs, d_pk_off + i0, st, n_launch); break;
          default: break;
       }
       if (rc) return rc;

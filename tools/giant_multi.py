@@ -11,7 +11,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 rows = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
 max_iter = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
 q = api.Quantifier(max_iter=max_iter)
-q.synth_giant(list(range(n)), rows)
+iso_lo, iso_hi = int(os.environ.get("ISO_LO", 500)), int(os.environ.get("ISO_HI", 800))
+q.synth_giant(list(range(n)), rows, iso_lo=iso_lo, iso_hi=iso_hi)
 for _ in range(2):
     q.solve(rows * n)
 q.finalize_tpm(q.fpkm_sum())
