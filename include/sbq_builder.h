@@ -117,6 +117,20 @@ int  sbq_set_insert_model(sbq_ctx*, const sbq_insert_model* model, int32_t read_
 int  sbq_submit_deferred(sbq_ctx*, const sbq_table* const* tables, int64_t n_tables);
 int  sbq_fetch_alpha(sbq_ctx*, double* alpha);
 
+/* Class assignment ON THE DEVICE (strawberry_b200/csrc/sbq_rawbuild.cuh). sbq_submit_raw queues one locus as
+ * the reference's LocusContext constructor receives it - the same sbq_locus_input sbq_build_locus takes (read_len and the
+ * insert model come from sbq_set_insert_model; defer_weights is ignored) - and sbq_upload then builds the whole class table of
+ * the batch on the GPU: compatibility (Contig::is_compatible), class coordinates (overlap_exons), first-seen class ids,
+ * code-blind set semantics of ExonBin::_frags, float class masses, the class x isoform CSR and the weight descriptors that
+ * weights_kernel turns into alpha. Integer results are bit-identical to sbq_build_locus (tests/test_gpu_rawbuild.py). A batch
+ * is either all raw loci or none; raw batches are single-device. What the kernels cannot reproduce bit-exactly - fragment
+ * masses that are not multiples of 1/2 (--allow-multimapped-hits), a hit touching more than 16 exon segments, a class spanning
+ * more than 32 segments of an isoform - makes sbq_upload return SBQ_ERR_UNSUPPORTED: use sbq_build_locus for such a batch.
+ * sbq_fetch_raw_classes (tests) copies the device-built table out; the CSR comes from sbq_fetch_batch. */
+int  sbq_submit_raw(sbq_ctx*, const sbq_locus_input* in);
+int  sbq_fetch_raw_classes(sbq_ctx*, int32_t* hit_class, uint8_t* hit_ncoord, uint16_t* hit_coords, int64_t* class_rep, float* class_mass,
+                           int32_t* class_nfrag);
+
 /* hit_class[n_hit]: class id of every input hit (the ExonBin whose _frags set it was offered to), -1 for hits
  * that were dropped (ref_id -1) or are compatible with no isoform. */
 int  sbq_table_hit_classes(const sbq_table*, int32_t* hit_class);

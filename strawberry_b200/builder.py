@@ -15,7 +15,8 @@ CIG_M, CIG_I, CIG_D, CIG_N, CIG_S = 0, 1, 2, 3, 4
 
 BUILDER_SYMBOLS = ["sbq_build_locus", "sbq_table_free", "sbq_table_locus", "sbq_table_get_dims", "sbq_table_segments",
                    "sbq_table_iso_segments", "sbq_table_classes", "sbq_table_hit_classes", "sbq_table_weight_desc",
-                   "sbq_set_insert_model", "sbq_submit_deferred", "sbq_fetch_alpha", "sbq_pair_features", "sbq_effective_len", "sbq_insert_pdf"]
+                   "sbq_set_insert_model", "sbq_submit_deferred", "sbq_fetch_alpha", "sbq_pair_features", "sbq_effective_len", "sbq_insert_pdf",
+                   "sbq_submit_raw", "sbq_fetch_raw_classes"]
 
 
 class InsertModel(ctypes.Structure):
@@ -53,6 +54,8 @@ def _lib():
         L.sbq_pair_features.argtypes = [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                         ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]
+        L.sbq_submit_raw.argtypes = [ctypes.c_void_p, ctypes.POINTER(LocusInput)]
+        L.sbq_fetch_raw_classes.argtypes = [ctypes.c_void_p] * 7
         L.sbq_effective_len.restype = ctypes.c_int32
         L.sbq_effective_len.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
         L.sbq_insert_pdf.restype = ctypes.c_double
@@ -185,3 +188,29 @@ def build_locus(transcripts, hits, *, read_len, model=None, long_read=False, ref
     else:
         L.sbq_table_free(h)
     return out
+
+
+def submit_raw(q, transcripts, hits, *, read_len, long_read=False, ref_ids=None):
+    """Queue one locus for class assignment ON THE DEVICE (sbq_submit_raw): same inputs as build_locus; the insert model and
+    read length come from q.set_insert_model(). The whole class table of the batch is built by q.upload()."""
+    L = _lib()
+    ip, io, il, ic = _flatten(transcripts)
+    hp, ho, hl, hc = _flatten([f for _, f in hits])
+    mass = np.asarray([m for m, _ in hits], np.float64)
+    rid = np.asarray(ref_ids, np.int32) if ref_ids is not None else None
+    inp = LocusInput(len(transcripts), _p(ip), _p(io), _p(il), _p(ic), len(hits), hp.ctypes.data, _p(ho), _p(hl), _p(hc),
+                     _p(mass), _p(rid) if rid is not None else None, int(read_len), int(long_read), 1)
+    q._chk(L.sbq_submit_raw(q._h, ctypes.byref(inp)))
+
+
+def fetch_raw_classes(q, n_hit):
+    """Device-built class table of the last raw upload (tests): per hit class id / touched segments, per class representative
+    hit, float mass and member count."""
+    L = _lib()
+    st = q.stats()
+    R = st["n_row"]
+    hit_class, ncoord = np.full(max(n_hit, 1), -1, np.int32), np.zeros(max(n_hit, 1), np.uint8)
+    coords = np.zeros((max(n_hit, 1), 16), np.uint16)
+    rep, mass, nfrag = np.zeros(max(R, 1), np.int64), np.zeros(max(R, 1), np.float32), np.zeros(max(R, 1), np.int32)
+    q._chk(L.sbq_fetch_raw_classes(q._h, hit_class.ctypes.data, ncoord.ctypes.data, coords.ctypes.data, rep.ctypes.data, mass.ctypes.data, nfrag.ctypes.data))
+    return dict(hit_class=hit_class[:n_hit], ncoord=ncoord[:n_hit], coords=coords[:n_hit], class_rep=rep[:R], class_mass=mass[:R], class_nfrag=nfrag[:R])

@@ -29,6 +29,7 @@
 #include "sbq_bias.cuh"
 #include "sbq_weights.cuh"
 #include "sbq_synth.cuh"
+#include "sbq_rawbuild.cuh"
 
 using namespace sbq;
 
@@ -167,6 +168,21 @@ struct sbq_ctx {
    DevBuf d_weights;
    double weights_ms = 0.0;
 
+   // raw loci (class assignment on the device, sbq_rawbuild.cuh): flattened feature lists of hits and isoforms + the static
+   // per-locus tables (segments, isoform segment lists) staged on the host until sbq_upload
+   struct RawStage {
+      std::vector<int32_t> hit_locus, hit_ref, iso_seg;
+      std::vector<int64_t> hit_feat_ptr{0}, iso_feat_ptr{0}, loc_hit_off{0}, loc_seg_off{0}, iso_seg_ptr{0};
+      std::vector<uint32_t> hf_off, hf_len, if_off, if_len, seg_left, seg_right;
+      std::vector<uint8_t> hf_code, if_code;
+      std::vector<float> hit_mass;
+      int long_read = 0;
+      void clear() { *this = RawStage(); }
+   } raw;
+   bool raw_mode = false;
+   DevBuf d_raw, d_raw2;
+   RawBatch rb{};                    // device view of the last raw upload (tests fetch the class table through it)
+
    // plan
    int force_tier = 0, force_cluster = 0;
    std::vector<int32_t> warp_list, grid_list;
@@ -266,6 +282,8 @@ void reset_batch(sbq_ctx* c) {
    c->have_cov = false;
    c->h_cov.clear();
    c->deferred = 0;
+   c->raw.clear();
+   c->raw_mode = false;
    c->h_wseg.clear(); c->h_wn.clear(); c->h_wmask.clear(); c->h_wpool.clear(); c->h_wlen.clear(); c->h_wpool_off.clear();
    c->resident = c->solved = c->downloaded = false;
 }
@@ -684,7 +702,7 @@ void sbq_destroy(sbq_ctx* c) {
    c->h_lists.release();
    c->r_theta.release(); c->r_fpkm.release(); c->r_frac.release(); c->r_tpm.release();
    c->r_locus_fpkm.release(); c->r_keep.release(); c->r_iters.release(); c->r_status.release(); c->r_frags.release(); c->d_frags.release();
-   c->d_in.release(); c->d_out.release(); c->d_lists.release(); c->d_grid_scratch.release(); c->d_col16.release(); c->d_rowrec.release(); c->d_csc.release(); c->d_synth.release(); c->d_pk.release(); c->d_bias.release();
+   c->d_in.release(); c->d_out.release(); c->d_lists.release(); c->d_grid_scratch.release(); c->d_col16.release(); c->d_rowrec.release(); c->d_csc.release(); c->d_synth.release(); c->d_pk.release(); c->d_raw.release(); c->d_raw2.release(); c->d_bias.release();
    c->h_cov.release(); c->r_beta.release(); c->r_outer.release();
    c->h_wseg.release(); c->h_wn.release(); c->h_wmask.release(); c->h_wpool.release(); c->h_wlen.release(); c->h_wpool_off.release(); c->d_weights.release();
    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -814,6 +832,8 @@ int sbq_validate(sbq_ctx* c) {
 //   3. the weights of everything else (the gaps between the ranges of step 2).
 // sbq_solve makes every launch wait for its own event only, so the largest loci start iterating while the rest of the batch
 // is still crossing PCIe. Nothing is synchronised here: the host arrays must stay valid until upload_finish / the solve.
+static int raw_upload(sbq_ctx* c);   // raw loci: class assignment on the device (defined further down)
+
 static int upload_begin(sbq_ctx* c) {
    CU(cudaSetDevice(c->device));
    if (c->upload_pending) {
@@ -933,7 +953,7 @@ extern "C" {
 
 int sbq_upload_begin(sbq_ctx* c) {
    if (!c) return SBQ_ERR_INVALID;
-   if (c->multi || c->deferred == 1 || c->cfg.bias_mode == 1) return sbq_upload(c);   // these paths have extra stages: synchronous upload
+   if (c->multi || c->deferred == 1 || c->raw_mode || c->cfg.bias_mode == 1) return sbq_upload(c);   // these paths have extra stages: synchronous upload
    std::lock_guard<std::mutex> lk(c->mu);
    return upload_begin(c);
 }
@@ -942,6 +962,10 @@ int sbq_upload(sbq_ctx* c) {
    if (!c) return SBQ_ERR_INVALID;
    if (c->multi) return multi_upload(c);
    std::lock_guard<std::mutex> lk(c->mu);
+   if (c->raw_mode) {
+      if (c->n_loci == 0) return fail(c, SBQ_ERR_STATE, "nothing submitted");
+      return raw_upload(c);
+   }
    {
       int rc = upload_begin(c);
       if (!rc) rc = upload_wait(c);   // borrowed host arrays may be released after this returns
@@ -1409,6 +1433,300 @@ int sbq_submit_deferred(sbq_ctx* c, const sbq_table* const* tables, int64_t n_ta
       }
       c->deferred = 1;
    }
+   return SBQ_SUCCESS;
+}
+
+// ---- raw loci: fragment-class assignment on the device (sbq_rawbuild.cuh) ---------------------------------------------
+int sbq_submit_raw(sbq_ctx* c, const sbq_locus_input* in) {
+   if (!c || !in || in->n_iso < 1 || in->n_hit < 0 || !in->iso_feat_ptr || (in->n_hit > 0 && (!in->hit_feat_ptr || !in->hit_mass))) return SBQ_ERR_INVALID;
+   if (c->multi) return fail(c, SBQ_ERR_UNSUPPORTED, "raw loci are single-device");
+   if (c->cfg.bias_mode) return fail(c, SBQ_ERR_UNSUPPORTED, "raw loci carry no covariates");
+   if (in->n_iso > SBQ_MAX_ISO) return fail(c, SBQ_ERR_UNSUPPORTED, "%d isoforms > SBQ_MAX_ISO", in->n_iso);
+   // static part of the class table on the host (cheap, O(exons + T S)): disjoint exon segments, isoform segment lists, lengths
+   sbq_locus_input st = *in;
+   st.n_hit = 0;
+   st.defer_weights = 1;
+   sbq_table* tb = nullptr;
+   sbq_insert_model dummy{0, 0, 0, nullptr, 0, 200.0, 20.0};
+   int rc = sbq_build_locus(&st, &dummy, &tb);
+   if (rc) return fail(c, rc, "sbq_build_locus (static part) failed");
+   sbq_table_dims d;
+   sbq_table_get_dims(tb, &d);
+   sbq_locus L;
+   sbq_table_locus(tb, &L);
+   std::lock_guard<std::mutex> lk(c->mu);
+   if (c->host_released || (c->n_loci > 0 && !c->raw_mode)) { sbq_table_free(tb); return fail(c, SBQ_ERR_STATE, "a batch is either all raw loci or none"); }
+   if (c->n_loci > 0 && c->raw.long_read != (in->long_read ? 1 : 0)) { sbq_table_free(tb); return fail(c, SBQ_ERR_STATE, "long_read must be the same for every raw locus of a batch"); }
+   if (d.n_seg > 65535) { sbq_table_free(tb); return fail(c, SBQ_ERR_UNSUPPORTED, "more than 65535 exon segments in one locus"); }
+   auto& r = c->raw;
+   r.long_read = in->long_read ? 1 : 0;
+   const int32_t locus = (int32_t)c->n_loci;
+   std::vector<uint32_t> sl(d.n_seg), sr(d.n_seg);
+   std::vector<int32_t> isp(d.n_iso + 1), isg;
+   sbq_table_segments(tb, sl.data(), sr.data());
+   sbq_table_iso_segments(tb, isp.data(), nullptr);
+   isg.resize(isp[d.n_iso]);
+   sbq_table_iso_segments(tb, nullptr, isg.data());
+   r.seg_left.insert(r.seg_left.end(), sl.begin(), sl.end());
+   r.seg_right.insert(r.seg_right.end(), sr.begin(), sr.end());
+   r.loc_seg_off.push_back((int64_t)r.seg_left.size());
+   const int64_t seg_base = (int64_t)r.iso_seg.size();
+   r.iso_seg.insert(r.iso_seg.end(), isg.begin(), isg.end());
+   for (int t = 1; t <= d.n_iso; ++t) r.iso_seg_ptr.push_back(seg_base + isp[t]);
+   const int64_t if_base = (int64_t)r.if_off.size();
+   const int nif = in->iso_feat_ptr[in->n_iso];
+   r.if_off.insert(r.if_off.end(), in->iso_feat_off, in->iso_feat_off + nif);
+   r.if_len.insert(r.if_len.end(), in->iso_feat_len, in->iso_feat_len + nif);
+   r.if_code.insert(r.if_code.end(), in->iso_feat_code, in->iso_feat_code + nif);
+   for (int t = 1; t <= in->n_iso; ++t) r.iso_feat_ptr.push_back(if_base + in->iso_feat_ptr[t]);
+   const int64_t hf_base = (int64_t)r.hf_off.size();
+   const int nhf = in->n_hit > 0 ? in->hit_feat_ptr[in->n_hit] : 0;
+   if (nhf) {
+      r.hf_off.insert(r.hf_off.end(), in->hit_feat_off, in->hit_feat_off + nhf);
+      r.hf_len.insert(r.hf_len.end(), in->hit_feat_len, in->hit_feat_len + nhf);
+      r.hf_code.insert(r.hf_code.end(), in->hit_feat_code, in->hit_feat_code + nhf);
+   }
+   for (int h = 0; h < in->n_hit; ++h) {
+      r.hit_feat_ptr.push_back(hf_base + in->hit_feat_ptr[h + 1]);
+      r.hit_locus.push_back(locus);
+      r.hit_mass.push_back((float)in->hit_mass[h]);
+      r.hit_ref.push_back(in->hit_ref_id ? in->hit_ref_id[h] : 0);
+   }
+   r.loc_hit_off.push_back((int64_t)r.hit_locus.size());
+   cudaSetDevice(c->device);
+   if ((rc = ensure_origin(c))) { sbq_table_free(tb); return rc; }
+   c->n_iso += d.n_iso;
+   c->n_loci += 1;
+   bool ok = c->h_loc_iso_off.append(&c->n_iso, 1) && c->h_iso_len.append(L.iso_len, d.n_iso);
+   sbq_table_free(tb);
+   if (!ok) return fail(c, SBQ_ERR_NOMEM, "pinned staging");
+   c->raw_mode = true;
+   c->deferred = 1;
+   c->resident = c->solved = c->downloaded = false;
+   return SBQ_SUCCESS;
+}
+
+} // extern "C" (reopened below)
+
+namespace {
+int rb_scan(cudaStream_t st, const int32_t* v, int64_t n, long long* block_tmp, int64_t* out) {
+   const int nb = (int)((n + RB_SCAN_BLOCK - 1) / RB_SCAN_BLOCK);
+   if (n == 0) return cudaMemsetAsync(out, 0, 8, st) == cudaSuccess ? 0 : -3;
+   rb_scan_sums_kernel<<<nb, 1024, 0, st>>>(v, n, block_tmp);
+   synth_scan_blocks_kernel<<<1, 1024, 0, st>>>(block_tmp, nb);
+   rb_scan_fill_kernel<<<nb, 1024, 0, st>>>(v, n, block_tmp, out);
+   return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+}  // namespace
+
+// Upload of a raw batch: feature lists to the device, class assignment there, CSR + weight descriptors + alpha on the device.
+static int raw_upload(sbq_ctx* c) {
+   CU(cudaSetDevice(c->device));
+   if (!c->have_model && !c->raw.long_read) return fail(c, SBQ_ERR_STATE, "raw loci need sbq_set_insert_model()");
+   auto& r = c->raw;
+   const int64_t L = c->n_loci, H = (int64_t)r.hit_locus.size(), T = c->n_iso, S = (int64_t)r.seg_left.size();
+   const int64_t* lio = c->h_loc_iso_off.p;
+   std::vector<int64_t> cm_off(L + 1, 0), tab_off(L + 1, 0);
+   for (int64_t l = 0; l < L; ++l) {
+      const int64_t Hl = r.loc_hit_off[l + 1] - r.loc_hit_off[l], W = (lio[l + 1] - lio[l] + 31) / 32;
+      cm_off[l + 1] = cm_off[l] + Hl * W;
+      int64_t cap = 8;
+      while (cap < 2 * Hl) cap <<= 1;
+      tab_off[l + 1] = tab_off[l] + cap;
+   }
+   const int64_t CM = cm_off[L], TAB = tab_off[L];
+   const int n_scan = (int)((std::max<int64_t>(H, 1) + RB_SCAN_BLOCK - 1) / RB_SCAN_BLOCK);
+   // ---- carve inputs + workspace
+   size_t need = 0;
+   auto sz = [&](size_t bytes) { const size_t o = need; need += align_up(bytes + 16); return o; };
+   const size_t o_hl = sz(H * 4), o_hfp = sz((H + 1) * 8), o_hfo = sz(r.hf_off.size() * 4), o_hfl = sz(r.hf_len.size() * 4), o_hfc = sz(r.hf_code.size());
+   const size_t o_hm = sz(H * 4), o_hr = sz(H * 4), o_lho = sz((L + 1) * 8), o_lio = sz((L + 1) * 8), o_lso = sz((L + 1) * 8);
+   const size_t o_ifp = sz((T + 1) * 8), o_ifo = sz(r.if_off.size() * 4), o_ifl = sz(r.if_len.size() * 4), o_ifc = sz(r.if_code.size());
+   const size_t o_sl = sz(S * 4), o_sr = sz(S * 4), o_isp = sz((T + 1) * 8), o_isg = sz(r.iso_seg.size() * 4), o_il = sz(T * 4);
+   const size_t o_co = sz(H * RB_MAXC * 2), o_nc = sz(H), o_va = sz(H), o_ch = sz(H * 8), o_fh = sz(H * 8), o_cmo = sz((L + 1) * 8), o_cm = sz(CM * 4);
+   const size_t o_to = sz((L + 1) * 8), o_k1 = sz(TAB * 8), o_m1 = sz(TAB * 4), o_s1 = sz(H * 4), o_k2 = sz(TAB * 8), o_m2 = sz(TAB * 4), o_s2 = sz(H * 4);
+   const size_t o_ir = sz(H * 4), o_cp = sz((H + 1) * 8), o_hc = sz(H * 4), o_fl = sz(64), o_bs = sz((size_t)n_scan * 8 + 8), o_g = sz((L + 1) * 8);
+   if (!c->d_raw.reserve(need)) return fail(c, SBQ_ERR_NOMEM, "device allocation failed (raw batch, %zu MB)", need >> 20);
+   char* base = (char*)c->d_raw.p;
+   cudaStream_t st = c->stream;
+   CU(cudaEventRecord(c->ev[0], st));
+   auto up = [&](size_t off, const void* src, size_t bytes) -> int {
+      if (bytes) CU(cudaMemcpyAsync(base + off, src, bytes, cudaMemcpyHostToDevice, st));
+      return 0;
+   };
+   int rc = 0;
+   rc |= up(o_hl, r.hit_locus.data(), H * 4); rc |= up(o_hfp, r.hit_feat_ptr.data(), (H + 1) * 8); rc |= up(o_hfo, r.hf_off.data(), r.hf_off.size() * 4);
+   rc |= up(o_hfl, r.hf_len.data(), r.hf_len.size() * 4); rc |= up(o_hfc, r.hf_code.data(), r.hf_code.size()); rc |= up(o_hm, r.hit_mass.data(), H * 4);
+   rc |= up(o_hr, r.hit_ref.data(), H * 4); rc |= up(o_lho, r.loc_hit_off.data(), (L + 1) * 8); rc |= up(o_lio, lio, (L + 1) * 8);
+   rc |= up(o_lso, r.loc_seg_off.data(), (L + 1) * 8); rc |= up(o_ifp, r.iso_feat_ptr.data(), (T + 1) * 8); rc |= up(o_ifo, r.if_off.data(), r.if_off.size() * 4);
+   rc |= up(o_ifl, r.if_len.data(), r.if_len.size() * 4); rc |= up(o_ifc, r.if_code.data(), r.if_code.size()); rc |= up(o_sl, r.seg_left.data(), S * 4);
+   rc |= up(o_sr, r.seg_right.data(), S * 4); rc |= up(o_isp, r.iso_seg_ptr.data(), (T + 1) * 8); rc |= up(o_isg, r.iso_seg.data(), r.iso_seg.size() * 4);
+   rc |= up(o_il, c->h_iso_len.p, T * 4); rc |= up(o_cmo, cm_off.data(), (L + 1) * 8); rc |= up(o_to, tab_off.data(), (L + 1) * 8);
+   if (rc) return SBQ_ERR_CUDA;
+   RawBatch& b = c->rb;
+   b = RawBatch{};
+   b.n_hit = H; b.n_loci = (int32_t)L; b.long_read = r.long_read;
+   b.hit_locus = (const int32_t*)(base + o_hl); b.hit_feat_ptr = (const int64_t*)(base + o_hfp); b.hf_off = (const uint32_t*)(base + o_hfo);
+   b.hf_len = (const uint32_t*)(base + o_hfl); b.hf_code = (const uint8_t*)(base + o_hfc); b.hit_mass = (const float*)(base + o_hm);
+   b.hit_ref = (const int32_t*)(base + o_hr); b.loc_hit_off = (const int64_t*)(base + o_lho); b.loc_iso_off = (const int64_t*)(base + o_lio);
+   b.loc_seg_off = (const int64_t*)(base + o_lso); b.iso_feat_ptr = (const int64_t*)(base + o_ifp); b.if_off = (const uint32_t*)(base + o_ifo);
+   b.if_len = (const uint32_t*)(base + o_ifl); b.if_code = (const uint8_t*)(base + o_ifc); b.seg_left = (const uint32_t*)(base + o_sl);
+   b.seg_right = (const uint32_t*)(base + o_sr); b.iso_seg_ptr = (const int64_t*)(base + o_isp); b.iso_seg = (const int32_t*)(base + o_isg);
+   b.iso_len = (const int32_t*)(base + o_il);
+   b.coords = (uint16_t*)(base + o_co); b.ncoord = (uint8_t*)(base + o_nc); b.valid = (uint8_t*)(base + o_va); b.chash = (unsigned long long*)(base + o_ch);
+   b.fhash = (unsigned long long*)(base + o_fh); b.loc_cm_off = (const int64_t*)(base + o_cmo); b.cm = (uint32_t*)(base + o_cm);
+   b.loc_tab_off = (const int64_t*)(base + o_to); b.keys1 = (unsigned long long*)(base + o_k1); b.min1 = (uint32_t*)(base + o_m1); b.slot1 = (uint32_t*)(base + o_s1);
+   b.keys2 = (unsigned long long*)(base + o_k2); b.min2 = (uint32_t*)(base + o_m2); b.slot2 = (uint32_t*)(base + o_s2);
+   b.is_rep = (int32_t*)(base + o_ir); b.cls_prefix = (int64_t*)(base + o_cp); b.hit_class = (int32_t*)(base + o_hc); b.flags = (int*)(base + o_fl);
+   long long* d_bs = (long long*)(base + o_bs);
+   int64_t* d_gather = (int64_t*)(base + o_g);
+   CU(cudaMemsetAsync(base + o_k1, 0xff, TAB * 8, st));
+   CU(cudaMemsetAsync(base + o_m1, 0xff, TAB * 4, st));
+   CU(cudaMemsetAsync(base + o_k2, 0xff, TAB * 8, st));
+   CU(cudaMemsetAsync(base + o_m2, 0xff, TAB * 4, st));
+   CU(cudaMemsetAsync(b.flags, 0, 64, st));
+   const int nbk = std::max(1, std::min<int>((int)((H + 127) / 128), c->prop.multiProcessorCount * 16));
+   auto check_flags = [&](const char* where) -> int {
+      int f = 0;
+      CU(cudaMemcpyAsync(&f, b.flags, sizeof f, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      if (f) return fail(c, SBQ_ERR_UNSUPPORTED, "device class assignment refused the batch (%s):%s%s%s%s - use the host builder (sbq_build_locus) for it", where,
+                         f & RB_FLAG_COORDS ? " a hit touches more than 16 exon segments;" : "", f & RB_FLAG_COLLISION ? " 64-bit hash collision;" : "",
+                         f & RB_FLAG_MASS ? " fragment masses are not multiples of 1/2 (or a class holds >= 2^23): the float sum would depend on the set order;" : "",
+                         f & RB_FLAG_NSEG ? " a class spans more than 32 segments of an isoform;" : "");
+      return 0;
+   };
+   if (H) {
+      raw_hit_kernel<<<nbk, 128, 0, st>>>(b);
+      raw_class_insert_kernel<<<nbk, 256, 0, st>>>(b);
+      raw_class_rep_kernel<<<nbk, 256, 0, st>>>(b);
+      CU(cudaGetLastError());
+   }
+   if (rb_scan(st, b.is_rep, H, d_bs, b.cls_prefix)) return fail(c, SBQ_ERR_CUDA, "scan failed");
+   // ---- round trip 1: classes per locus
+   rb_gather_kernel<<<(unsigned)((L + 1 + 255) / 256), 256, 0, st>>>(b.cls_prefix, b.loc_hit_off, L + 1, d_gather);
+   std::vector<int64_t> cls_off(L + 1);
+   CU(cudaMemcpyAsync(cls_off.data(), d_gather, (L + 1) * 8, cudaMemcpyDeviceToHost, st));
+   if ((rc = check_flags("hits"))) return rc;
+   const int64_t R = cls_off[L];
+   std::vector<int64_t> cmask_off(L + 1, 0);
+   std::vector<int32_t> class_locus((size_t)R);
+   for (int64_t l = 0; l < L; ++l) {
+      const int64_t W = (lio[l + 1] - lio[l] + 31) / 32;
+      cmask_off[l + 1] = cmask_off[l] + (cls_off[l + 1] - cls_off[l]) * W;
+      for (int64_t x = cls_off[l]; x < cls_off[l + 1]; ++x) class_locus[x] = (int32_t)l;
+   }
+   size_t need2 = 0;
+   auto sz2 = [&](size_t bytes) { const size_t o = need2; need2 += align_up(bytes + 16); return o; };
+   const int n_scan2 = (int)((std::max<int64_t>(R, 1) + RB_SCAN_BLOCK - 1) / RB_SCAN_BLOCK);
+   const size_t p_co = sz2((L + 1) * 8), p_mo = sz2((L + 1) * 8), p_cl = sz2(R * 4), p_rep = sz2(R * 8), p_ms = sz2(R * 4), p_nf = sz2(R * 4), p_cmk = sz2(cmask_off[L] * 4),
+                p_nz = sz2(R * 4), p_rp = sz2((R + 1) * 8), p_bs = sz2((size_t)n_scan2 * 8 + 8), p_g = sz2((L + 1) * 8);
+   if (!c->d_raw2.reserve(need2)) return fail(c, SBQ_ERR_NOMEM, "device allocation failed (class arrays)");
+   char* base2 = (char*)c->d_raw2.p;
+   CU(cudaMemcpyAsync(base2 + p_co, cls_off.data(), (L + 1) * 8, cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(base2 + p_mo, cmask_off.data(), (L + 1) * 8, cudaMemcpyHostToDevice, st));
+   if (R) CU(cudaMemcpyAsync(base2 + p_cl, class_locus.data(), R * 4, cudaMemcpyHostToDevice, st));
+   CU(cudaMemsetAsync(base2 + p_ms, 0, align_up(R * 4 + 16), st));
+   CU(cudaMemsetAsync(base2 + p_nf, 0, align_up(R * 4 + 16), st));
+   CU(cudaMemsetAsync(base2 + p_cmk, 0, align_up(cmask_off[L] * 4 + 16), st));
+   b.loc_cls_off = (const int64_t*)(base2 + p_co); b.loc_cmask_off = (const int64_t*)(base2 + p_mo); b.class_rep = (int64_t*)(base2 + p_rep);
+   b.class_mass = (float*)(base2 + p_ms); b.class_nfrag = (int32_t*)(base2 + p_nf); b.cmask = (uint32_t*)(base2 + p_cmk); b.class_nnz = (int32_t*)(base2 + p_nz);
+   const int32_t* d_class_locus = (const int32_t*)(base2 + p_cl);
+   int64_t* d_rp_tmp = (int64_t*)(base2 + p_rp);
+   const int nbc = std::max(1, std::min<int>((int)((R + 127) / 128), c->prop.multiProcessorCount * 16));
+   if (H) {
+      raw_member_kernel<<<nbk, 256, 0, st>>>(b);
+      raw_mass_kernel<<<nbk, 256, 0, st>>>(b);
+   }
+   if (R) raw_nnz_kernel<<<nbc, 256, 0, st>>>(b, R, d_class_locus);
+   CU(cudaGetLastError());
+   if (rb_scan(st, b.class_nnz, R, (long long*)(base2 + p_bs), d_rp_tmp)) return fail(c, SBQ_ERR_CUDA, "scan failed");
+   // ---- round trip 2: non-zeros per locus
+   rb_gather_kernel<<<(unsigned)((L + 1 + 255) / 256), 256, 0, st>>>(d_rp_tmp, b.loc_cls_off, L + 1, (int64_t*)(base2 + p_g));
+   std::vector<int64_t> nz_off(L + 1);
+   CU(cudaMemcpyAsync(nz_off.data(), base2 + p_g, (L + 1) * 8, cudaMemcpyDeviceToHost, st));
+   if ((rc = check_flags("classes"))) return rc;
+   c->n_row = R;
+   c->nnz = nz_off[L];
+   if ((rc = alloc_device(c))) return rc;
+   DevParams& dp = c->dp;
+   CU(cudaMemcpyAsync(const_cast<int64_t*>(dp.loc_row_off), cls_off.data(), (L + 1) * 8, cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(const_cast<int64_t*>(dp.loc_iso_off), lio, (L + 1) * 8, cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(const_cast<int64_t*>(dp.row_ptr), d_rp_tmp, (R + 1) * 8, cudaMemcpyDeviceToDevice, st));
+   CU(cudaMemcpyAsync(const_cast<int32_t*>(dp.iso_len), c->h_iso_len.p, T * 4, cudaMemcpyHostToDevice, st));
+   // ---- CSR rows, counts, weight descriptors; alpha by weights_kernel (the same kernel the deferred host tables use)
+   const int64_t nnz = c->nnz;
+   const size_t b_seg = align_up(nnz * 8 + 8), b_n = align_up(nnz + 8), b_m = align_up(nnz * 4 + 8), b_l = align_up(nnz * 4 + 8), b_pool = align_up((size_t)nnz * RB_POOL * 4 + 8),
+                b_emp = align_up(c->model_emp.size() * 8 + 8);
+   if (!c->d_weights.reserve(b_seg + b_n + b_m + b_l + b_pool + b_emp)) return fail(c, SBQ_ERR_NOMEM, "device allocation failed (weight descriptors)");
+   char* q = (char*)c->d_weights.p;
+   int64_t* d_seg = (int64_t*)q; q += b_seg;
+   uint8_t* d_n = (uint8_t*)q; q += b_n;
+   uint32_t* d_m = (uint32_t*)q; q += b_m;
+   int32_t* d_l = (int32_t*)q; q += b_l;
+   uint32_t* d_pool = (uint32_t*)q; q += b_pool;
+   double* d_emp = (double*)q;
+   if (R) raw_fill_kernel<<<nbc, 128, 0, st>>>(b, R, d_class_locus, dp.row_ptr, const_cast<int32_t*>(dp.col), const_cast<double*>(dp.alpha), const_cast<int32_t*>(dp.count),
+                                               d_seg, d_n, d_m, d_l, d_pool);
+   CU(cudaGetLastError());
+   if ((rc = check_flags("weights"))) return rc;
+   CU(cudaEventRecord(c->ev[5], st));
+   if (!r.long_read && nnz) {
+      if (!c->model_emp.empty()) CU(cudaMemcpyAsync(d_emp, c->model_emp.data(), c->model_emp.size() * 8, cudaMemcpyHostToDevice, st));
+      WeightModel wm{c->model.use_emp, c->model.start_offset, c->model.end_offset, c->model.total_reads, d_emp, c->model.mean, c->model.sd, c->model_read_len};
+      const int blocks = std::max(1, std::min<int>((int)((nnz + 7) / 8), c->prop.multiProcessorCount * 16));
+      weights_kernel<<<blocks, 256, 0, st>>>(nnz, d_seg, d_n, d_m, d_l, d_pool, wm, const_cast<double*>(dp.alpha));
+      CU(cudaGetLastError());
+   }
+   CU(cudaEventRecord(c->ev[6], st));
+   // fragment totals, plan, work lists
+   if (!c->r_frags.reserve((size_t)L) || !c->d_frags.reserve(align_up((size_t)L * 8))) return fail(c, SBQ_ERR_NOMEM, "fragment-total buffers");
+   locus_frags_kernel<<<std::max(1, std::min<int>((int)((L + 7) / 8), c->prop.multiProcessorCount * 8)), 256, 0, st>>>(dp.loc_row_off, dp.count, L, (long long*)c->d_frags.p);
+   CU(cudaMemcpyAsync(c->r_frags.p, c->d_frags.p, (size_t)L * 8, cudaMemcpyDeviceToHost, st));
+   CU(cudaStreamSynchronize(st));
+   c->meta.resize((size_t)L);
+   for (int64_t l = 0; l < L; ++l) c->meta[l] = {nz_off[l + 1] - nz_off[l], c->r_frags.p[l], (int32_t)(cls_off[l + 1] - cls_off[l]), (int32_t)(lio[l + 1] - lio[l])};
+   if ((rc = plan(c))) return rc;
+   if (c->h_lists.n) CU(cudaMemcpyAsync(c->d_lists_p, c->h_lists.p, c->h_lists.n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+   if (!c->classes.empty()) {
+      if (!c->d_csc.reserve(align_up(c->nnz * 4 + 16))) return fail(c, SBQ_ERR_NOMEM, "device allocation failed (transposed-index scratch)");
+      dp.csc = (unsigned*)c->d_csc.p;
+   }
+   CU(cudaEventRecord(c->ev[1], st));
+   CU(cudaStreamSynchronize(st));
+   float ms = 0;
+   CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+   c->stats.upload_ms = ms;
+   CU(cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]));
+   c->stats.weights_ms = ms;
+   c->weights_ms = ms;
+   c->stats.h2d_bytes = (int64_t)(H * 20 + r.hf_off.size() * 9 + r.if_off.size() * 9 + S * 8 + r.iso_seg.size() * 4 + T * 20 + L * 40);
+   c->stats.n_loci = c->n_loci; c->stats.n_row = c->n_row; c->stats.n_iso = c->n_iso; c->stats.nnz = c->nnz;
+   c->resident = true;
+   c->col16_ready = false;
+   c->solved = c->downloaded = false;
+   return SBQ_SUCCESS;
+}
+
+extern "C" {
+
+// Tests: the device-built class table of the last raw upload. hit_class[n_hit] (local class id or -1), hit_ncoord[n_hit] and
+// hit_coords[n_hit][16] (segment indices a hit touches), class_rep[n_row] (representative hit, batch-wide index),
+// class_mass[n_row], class_nfrag[n_row]; the CSR itself comes from sbq_fetch_batch. Any pointer may be NULL.
+int sbq_fetch_raw_classes(sbq_ctx* c, int32_t* hit_class, uint8_t* hit_ncoord, uint16_t* hit_coords, int64_t* class_rep, float* class_mass, int32_t* class_nfrag) {
+   if (!c) return SBQ_ERR_INVALID;
+   std::lock_guard<std::mutex> lk(c->mu);
+   CU(cudaSetDevice(c->device));
+   if (!c->resident || !c->raw_mode) return fail(c, SBQ_ERR_STATE, "sbq_fetch_raw_classes needs an uploaded raw batch");
+   const RawBatch& b = c->rb;
+   cudaStream_t st = c->stream;
+   if (hit_class && b.n_hit) CU(cudaMemcpyAsync(hit_class, b.hit_class, b.n_hit * 4, cudaMemcpyDeviceToHost, st));
+   if (hit_ncoord && b.n_hit) CU(cudaMemcpyAsync(hit_ncoord, b.ncoord, b.n_hit, cudaMemcpyDeviceToHost, st));
+   if (hit_coords && b.n_hit) CU(cudaMemcpyAsync(hit_coords, b.coords, b.n_hit * RB_MAXC * 2, cudaMemcpyDeviceToHost, st));
+   if (class_rep && c->n_row) CU(cudaMemcpyAsync(class_rep, b.class_rep, c->n_row * 8, cudaMemcpyDeviceToHost, st));
+   if (class_mass && c->n_row) CU(cudaMemcpyAsync(class_mass, b.class_mass, c->n_row * 4, cudaMemcpyDeviceToHost, st));
+   if (class_nfrag && c->n_row) CU(cudaMemcpyAsync(class_nfrag, b.class_nfrag, c->n_row * 4, cudaMemcpyDeviceToHost, st));
+   CU(cudaStreamSynchronize(st));
    return SBQ_SUCCESS;
 }
 
