@@ -127,7 +127,7 @@ int  sbq_fetch_alpha(sbq_ctx*, double* alpha);
  * masses that are not multiples of 1/2 (--allow-multimapped-hits), a hit touching more than 16 exon segments, a class spanning
  * more than 32 segments of an isoform - makes sbq_upload return SBQ_ERR_UNSUPPORTED: use sbq_build_locus for such a batch.
  * sbq_fetch_raw_classes (tests) copies the device-built table out; the CSR comes from sbq_fetch_batch. */
-int  sbq_submit_raw(sbq_ctx*, const sbq_locus_input* in);
+int  sbq_submit_raw(sbq_ctx*, const sbq_locus_input* in, int64_t* locus_index /* may be NULL: position of the locus in the batch (submit order) */);
 int  sbq_fetch_raw_classes(sbq_ctx*, int32_t* hit_class, uint8_t* hit_ncoord, uint16_t* hit_coords, int64_t* class_rep, float* class_mass,
                            int32_t* class_nfrag);
 

@@ -33,6 +33,7 @@ struct TableDeleter {
 // weight setters on the same thread: the table built by the first call is handed to the second through this slot.
 thread_local unique_ptr<sbq_table, TableDeleter> tl_table;
 thread_local bool tl_deferred = false;      // the table of this thread's current locus was built with defer_weights = 1
+thread_local bool tl_raw = false;           // this thread's current locus was queued raw (class table built on the device)
 atomic<bool> g_model_set{false};
 
 mutex g_ctx_mu;
@@ -45,9 +46,10 @@ double g_insert_mean = 0.0;   // set from the Sample of the first locus, before 
 // the results of that locus. Per-locus mode (the default, used when the reference's own procSample drives) does both at once.
 enum { MODE_PER_LOCUS = 0, MODE_STAGE = 1, MODE_FINISH = 2 };
 int g_mode = MODE_PER_LOCUS;
-struct Staged { int64_t locus, iso_off; };
+struct Staged { int64_t locus, iso_off; };   // iso_off < 0: not known yet (raw loci submitted concurrently; filled by sbq_batch_run)
 unordered_map<const LocusContext*, Staged> g_staged;
 int64_t g_n_loci = 0, g_n_iso = 0;
+vector<int32_t> g_raw_niso;                    // isoforms of every raw locus by batch position
 vector<double> g_theta, g_fpkm, g_frac, g_tpm;
 vector<int32_t> g_keep, g_status;
 
@@ -133,6 +135,10 @@ void LocusContext::assign_exon_bin(const vector<Contig>& hits, const vector<Geno
                       (int32_t)hits.size(), hit_ptr.data(), hoff.data(), hlen.data(), hcode.data(), mass.data(), ref_ids.data(),
                       _read_len, long_read_sample ? 1 : 0, defer};
    tl_deferred = defer != 0;
+   // Class assignment on the device as well (sbq_submit_raw): the locus is queued as it is - flattened hits and isoforms - and
+   // the whole class table of the sample is built by CUDA kernels during sbq_upload. Fragment masses must be multiples of 1/2
+   // (true unless --allow-multimapped-hits), -f needs the table on the host; SBQ_HOST_CLASSES=1 keeps the host builder.
+   tl_raw = defer && use_only_unique_hits && !getenv("SBQ_HOST_CLASSES") && !(getenv("SBQ_N_GPUS") && atoi(getenv("SBQ_N_GPUS")) > 1);   // raw batches are single-device
    if (defer && !g_model_set.load()) {      // the context's insert model and read length (once per sample)
       lock_guard<mutex> lk(g_ctx_mu);
       if (!g_model_set.load()) {
@@ -141,6 +147,28 @@ void LocusContext::assign_exon_bin(const vector<Contig>& hits, const vector<Geno
          if (rcm != SBQ_SUCCESS) { fprintf(stderr, "libsbq: sbq_set_insert_model: %s\n", sbq_error_string(rcm)); exit(1); }
          g_model_set = true;
       }
+   }
+   if (tl_raw) {
+      const long long t_raw = now_ns();
+      sbq_ctx* ctx;
+      {
+         lock_guard<mutex> lk(g_ctx_mu);
+         ctx = context();
+      }
+      int64_t idx = -1;
+      const int rcr = sbq_submit_raw(ctx, &in, &idx);          // thread-safe; the static part of the table is built outside libsbq's lock
+      if (rcr != SBQ_SUCCESS) { fprintf(stderr, "libsbq: sbq_submit_raw: %s (%s)\n", sbq_error_string(rcr), sbq_last_error(ctx)); exit(1); }
+      {
+         lock_guard<mutex> lk(g_ctx_mu);
+         g_staged[this] = Staged{idx, -1};
+         if ((int64_t)g_raw_niso.size() <= idx) g_raw_niso.resize(idx + 1, 0);
+         g_raw_niso[idx] = (int32_t)_transcripts.size();
+         g_n_loci += 1;
+         g_n_iso += (int64_t)_transcripts.size();
+      }
+      g_tm.table_ns += now_ns() - t_raw;
+      g_tm.loci += 1;
+      return;                                  // exon_bins stay empty: nothing on the host needs them without -f
    }
    sbq_table* tb = nullptr;
    const long long t_build = now_ns();
@@ -175,6 +203,7 @@ void LocusContext::assign_exon_bin(const vector<Contig>& hits, const vector<Geno
 }
 
 static void weights_from_table(vector<ExonBin>& bins) {
+   if (tl_raw) return;                         // raw locus: there is no host table
    sbq_locus L;
    sbq_table_locus(tl_table.get(), &L);
    for (int c = 0; c < L.n_row; ++c)
@@ -190,6 +219,10 @@ bool LocusContext::estimate_abundances() {
    vector<double> theta(niso), fpkm(niso), frac(niso);
    vector<int32_t> keep(niso);
    int32_t status = 0;
+   if (g_mode == MODE_STAGE && tl_raw) {       // already queued by assign_exon_bin (sbq_submit_raw)
+      tl_raw = false;
+      return true;
+   }
    if (g_mode != MODE_FINISH) {
       const long long t0 = now_ns();
       vector<int64_t> row_ptr(1, 0);
@@ -276,6 +309,7 @@ void sbq_batch_begin() {
    lock_guard<mutex> lk(g_ctx_mu);
    g_mode = MODE_STAGE;
    g_staged.clear();
+   g_raw_niso.clear();
    g_n_loci = g_n_iso = 0;
    if (g_ctx) sbq_clear(g_ctx);
 }
@@ -285,6 +319,11 @@ void sbq_batch_run(int total_mapped_reads) {
    lock_guard<mutex> lk(g_ctx_mu);
    g_mode = MODE_FINISH;
    if (g_n_loci == 0) return;
+   if (!g_raw_niso.empty()) {                  // raw loci: isoform offsets from the batch positions libsbq assigned
+      vector<int64_t> off(g_raw_niso.size() + 1, 0);
+      for (size_t i = 0; i < g_raw_niso.size(); ++i) off[i + 1] = off[i] + g_raw_niso[i];
+      for (auto& kv : g_staged) kv.second.iso_off = off[kv.second.locus];
+   }
    const long long t0 = now_ns();
    sbq_ctx* c = context();
    g_theta.resize(g_n_iso); g_fpkm.resize(g_n_iso); g_frac.resize(g_n_iso); g_tpm.resize(g_n_iso); g_keep.resize(g_n_iso); g_status.resize(g_n_loci);

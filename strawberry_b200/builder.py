@@ -54,7 +54,7 @@ def _lib():
         L.sbq_pair_features.argtypes = [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                         ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]
-        L.sbq_submit_raw.argtypes = [ctypes.c_void_p, ctypes.POINTER(LocusInput)]
+        L.sbq_submit_raw.argtypes = [ctypes.c_void_p, ctypes.POINTER(LocusInput), ctypes.c_void_p]
         L.sbq_fetch_raw_classes.argtypes = [ctypes.c_void_p] * 7
         L.sbq_effective_len.restype = ctypes.c_int32
         L.sbq_effective_len.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
@@ -200,7 +200,7 @@ def submit_raw(q, transcripts, hits, *, read_len, long_read=False, ref_ids=None)
     rid = np.asarray(ref_ids, np.int32) if ref_ids is not None else None
     inp = LocusInput(len(transcripts), _p(ip), _p(io), _p(il), _p(ic), len(hits), hp.ctypes.data, _p(ho), _p(hl), _p(hc),
                      _p(mass), _p(rid) if rid is not None else None, int(read_len), int(long_read), 1)
-    q._chk(L.sbq_submit_raw(q._h, ctypes.byref(inp)))
+    q._chk(L.sbq_submit_raw(q._h, ctypes.byref(inp), None))
 
 
 def fetch_raw_classes(q, n_hit):

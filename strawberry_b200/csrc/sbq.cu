@@ -1437,7 +1437,7 @@ int sbq_submit_deferred(sbq_ctx* c, const sbq_table* const* tables, int64_t n_ta
 }
 
 // ---- raw loci: fragment-class assignment on the device (sbq_rawbuild.cuh) ---------------------------------------------
-int sbq_submit_raw(sbq_ctx* c, const sbq_locus_input* in) {
+int sbq_submit_raw(sbq_ctx* c, const sbq_locus_input* in, int64_t* locus_index) {
    if (!c || !in || in->n_iso < 1 || in->n_hit < 0 || !in->iso_feat_ptr || (in->n_hit > 0 && (!in->hit_feat_ptr || !in->hit_mass))) return SBQ_ERR_INVALID;
    if (c->multi) return fail(c, SBQ_ERR_UNSUPPORTED, "raw loci are single-device");
    if (c->cfg.bias_mode) return fail(c, SBQ_ERR_UNSUPPORTED, "raw loci carry no covariates");
@@ -1503,6 +1503,7 @@ int sbq_submit_raw(sbq_ctx* c, const sbq_locus_input* in) {
    c->raw_mode = true;
    c->deferred = 1;
    c->resident = c->solved = c->downloaded = false;
+   if (locus_index) *locus_index = locus;
    return SBQ_SUCCESS;
 }
 

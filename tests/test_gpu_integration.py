@@ -131,8 +131,9 @@ def test_batched_dropin_is_byte_exact(tmp_path):
     assert len(ref_gtf) > info["n_isoforms"] and len(ref_theta) > 100
     # single pass (the clusters of pass 1 are reused: SURVEY 8f.2, the default) and two passes over the BAM like the reference;
     # GPU class weights (default) and host class weights
-    for threads, env in ((1, {}), (4, {}), (1, {"SBQ_SINGLE_PASS": "0"}), (4, {"SBQ_SINGLE_PASS": "0", "SBQ_HOST_WEIGHTS": "1"})):
-        tag = f"b{threads}_{len(env)}"
+    # class assignment on the GPU (default) and in the host builder
+    for n, (threads, env) in enumerate(((1, {}), (4, {}), (1, {"SBQ_SINGLE_PASS": "0"}), (4, {"SBQ_SINGLE_PASS": "0", "SBQ_HOST_WEIGHTS": "1"}), (1, {"SBQ_HOST_CLASSES": "1"}))):
+        tag = f"b{n}"                       # (the program refuses to overwrite an existing output file)
         out, log = str(tmp_path / f"{tag}.gtf"), str(tmp_path / f"{tag}.log")
         run(BATCHED, bam, gtf, out, log, threads, **env)
         got = gtf_body(out)

@@ -48,6 +48,7 @@ def go(tag, binary, threads, **env):
 runs = [go("reference -p 1", "strawberry_ref_timed", 1), go(f"reference -p {nproc}", "strawberry_ref_timed", nproc),
         go("per-locus drop-in -p 1", "strawberry_sbq", 1), go("batched drop-in -p 1", "strawberry_sbq_batched", 1),
         go(f"batched drop-in -p {nproc}", "strawberry_sbq_batched", nproc),
+        go("batched drop-in -p 1, host class assignment", "strawberry_sbq_batched", 1, SBQ_HOST_CLASSES="1"),
         go("batched drop-in -p 1, two passes over the BAM", "strawberry_sbq_batched", 1, SBQ_SINGLE_PASS="0"),
         go("batched drop-in -p 1, two passes, host weights", "strawberry_sbq_batched", 1, SBQ_SINGLE_PASS="0", SBQ_HOST_WEIGHTS="1")]
 if n_gpu > 1:
