@@ -398,7 +398,7 @@ def main():
 
 # DRAM bytes per non-zero and EM pass of the giant-locus kernel, from `ncu --set full` captures of this kernel on this shape
 # (dram__bytes_read.sum + dram__bytes_write.sum of one launch / (passes x non-zeros)); see profiles/ for the capture files.
-GIANT_DRAM_BYTES_PER_NNZ_PASS = {"em_grid_dual_kernel": (10.63, "profiles/r01_grid_dual_ncu_summary.txt"),
+GIANT_DRAM_BYTES_PER_NNZ_PASS = {"em_grid_dual_kernel": (10.854, "profiles/r02_grid_dual_ncu_summary.txt"),
                                  "em_grid_tma_kernel": (10.34, "profiles/r01_grid_tma_ncu_summary.txt")}
 
 
