@@ -374,7 +374,7 @@ int plan(sbq_ctx* c) {
       // every T <= SBQ_MAX_ISO fits both the cluster tier (streaming accumulators) and the register-staged grid kernel;
       // the checks stay so that a future change of either limit degrades to the other tier instead of failing the upload
       if (tier == 3 && !grid_tier_supports((int)T)) tier = 2;
-      if (tier == 2 && cluster_stream_groups((int)T, SMEM_CAP, CL_NT) <= 0) {
+      if (tier == 2 && cluster_stream_groups((int)T, SMEM_CAP, CL_NT, 1, 0) <= 0) {
          if (!grid_tier_supports((int)T)) return fail(c, SBQ_ERR_UNSUPPORTED, "locus %lld: %lld isoforms fit no tier", (long long)l, (long long)T);
          tier = 3;
       }
@@ -397,7 +397,7 @@ int plan(sbq_ctx* c) {
          int cs = c->force_cluster ? c->force_cluster : cluster_size_for(nnz);
          int csi = cs == 1 ? 0 : cs == 2 ? 1 : cs == 4 ? 2 : cs == 8 ? 3 : 4;
          const size_t slice = cluster_slice_estimate(nnz, R, (int)T, cs);
-         const int bucket = cs == 1 ? smem_bucket(cluster_fixed_doubles((int)T) * sizeof(double) + slice + 256) : N_BUCKETS - 1;
+         const int bucket = cs == 1 ? smem_bucket(cluster_fixed_doubles((int)T, 1, slice) * sizeof(double) + slice + 256) : N_BUCKETS - 1;
          if (!slot[csi][bucket]) {
             tmp.push_back(LaunchClass{cs, BUCKET_NT[bucket], {}, 0, 0, 0, 0});
             slot[csi][bucket] = &tmp.back();
@@ -406,6 +406,9 @@ int plan(sbq_ctx* c) {
          lc->loci.push_back((int32_t)l);
          lc->max_iso = std::max(lc->max_iso, (int)T);
          lc->max_slice = std::max(lc->max_slice, slice);
+         // shared memory of the launch = the largest need of its loci (the need is not monotone in T: the exchange area of a
+         // narrow locus in a big cluster, CS x T, can exceed that of a wide one, 2T)
+         lc->smem = std::max(lc->smem, cluster_class_smem((int)T, slice, lc->lpr, cs));
       }
    }
    auto by_size = [&](int32_t a, int32_t b) { return nnz_of[a] != nnz_of[b] ? nnz_of[a] > nnz_of[b] : a < b; };
@@ -442,8 +445,7 @@ int plan(sbq_ctx* c) {
    }
    for (auto& lc : tmp) {
       std::sort(lc.loci.begin(), lc.loci.end(), by_size);
-      lc.smem = cluster_class_smem(lc.max_iso, lc.max_slice, lc.lpr);
-      if (cluster_stream_groups(lc.max_iso, lc.smem, lc.lpr) <= 0)
+      if (cluster_stream_groups(lc.max_iso, SMEM_CAP, lc.lpr, 1, 0) <= 0)
          return fail(c, SBQ_ERR_UNSUPPORTED, "locus with %d isoforms does not fit the cluster tier", lc.max_iso);
       c->classes.push_back(std::move(lc));
    }

@@ -892,7 +892,9 @@ em_grid_dual_kernel(DevParams p, const unsigned short* __restrict__ col16, RowRe
 // The kernel is bound by instruction latency, so it lives on warps per SM: 0.143 / 0.160 / 0.172 / 0.217 ms per pass with
 // 12 / 10 / 8 / 6 warps on the configs[3] shape, against 0.2045 ms for the TMA ring kernel. It is used where at least 8
 // warps fit (T <= ~1300; 12 warps up to T ~ 800).
-inline bool grid_dual_supports_iso(int T) { return T <= G6_MAX_ISO && G6Cfg<8>::fits(T, 1); }
+// default wherever the kernel can run: measured on 1 M rows x 48 non-zeros, even its 4-warp configuration (T = 2000: 0.32 of the HBM
+// peak, T = 1400 with 6 warps: 0.43) beats the TMA ring kernel (0.27 / 0.37), which remains for T > G6_MAX_ISO and dense rows
+inline bool grid_dual_supports_iso(int T) { return T <= G6_MAX_ISO && G6Cfg<4>::fits(T, 1); }
 inline bool grid_dual_possible(int T) { return T <= G6_MAX_ISO && G6Cfg<4>::fits(T, 1); }   // SBQ_GRID_DUAL=1 forces the kernel wherever it can run
 
 // warps per CTA for a locus of T isoforms: a function of the LOCUS alone (the launcher groups loci by it), so that neither the

@@ -310,11 +310,27 @@ constexpr int CL_NT = 512;           // threads per CTA of the cluster tier (sma
 constexpr int CL_NT_SMALL = 128;
 constexpr int CL_LPR_STREAM = 32;    // lanes per row of the streaming fallback
 
-__host__ __device__ inline size_t cluster_fixed_doubles(int T) { return (size_t)6 * T + 64; }   // th, theta x2, s_j, exchange area [2T+64]
+// Exchange of the partial theta' inside a cluster, two forms. All-to-all: every CTA broadcasts its row of T partials to all peers and
+// every CTA adds the CS rows itself - ONE blocking cluster barrier per iteration, but an exchange area of CS x T doubles. Owner form:
+// column j is reduced by CTA j / B, which pushes the result back - two barriers, 3T remote stores, 2T doubles. A locus gets the
+// all-to-all form when the CS x T partials are at most CL_A2A_MAX doubles AND its estimated slice, transposed index included, still
+// fits next to them (the index of the largest loci spills to L2 as it is: they keep the small exchange area). A function of the
+// locus alone (T, rows, non-zeros, CS), evaluated identically by the planner and the kernel.
+constexpr int CL_A2A_MAX = 4096;
+constexpr size_t CL_SMEM_CAP = 220 * 1024;   // dynamic shared memory a CTA asks for at most (227 KB usable, ~5.3 KB of them static)
+__host__ __device__ inline int cluster_a2a_stride(int T) { return (T + 1) & ~1; }                 // rows of the exchange area are 16-byte aligned
+__host__ __device__ inline bool cluster_a2a(int T, int cs, size_t slice_bytes) {
+   if (cs <= 1 || (long long)cs * cluster_a2a_stride(T) > CL_A2A_MAX) return false;
+   return ((size_t)4 * T + (size_t)cs * cluster_a2a_stride(T) + 64) * sizeof(double) + slice_bytes + 256 <= CL_SMEM_CAP;
+}
+// th, theta x2, s_j, exchange area ([CS][T] + 64 all-to-all, [2T+64] otherwise)
+__host__ __device__ inline size_t cluster_fixed_doubles(int T, int cs, size_t slice_bytes) {
+   return (size_t)4 * T + (cluster_a2a(T, cs, slice_bytes) ? (size_t)cs * cluster_a2a_stride(T) + 64 : (size_t)2 * T + 64);
+}
 
 // groups of the streaming fallback that fit next to the fixed arrays
-__host__ __device__ inline int cluster_stream_groups(int T, size_t smem_bytes, int nt = CL_NT) {
-   const long long budget = (long long)(smem_bytes / sizeof(double)) - (long long)cluster_fixed_doubles(T);
+__host__ __device__ inline int cluster_stream_groups(int T, size_t smem_bytes, int nt, int cs, size_t slice_bytes) {
+   const long long budget = (long long)(smem_bytes / sizeof(double)) - (long long)cluster_fixed_doubles(T, cs, slice_bytes);
    long long G = budget / (T > 0 ? T : 1);
    if (G > nt / CL_LPR_STREAM) G = nt / CL_LPR_STREAM;
    return (int)G;   // 0 => does not fit
@@ -333,9 +349,8 @@ __host__ __device__ inline size_t cluster_resident_bytes(size_t nnz_c, size_t nr
 // fixed arrays + the larger of (estimated largest resident slice, a full set of streaming accumulators). Host planner and
 // kernel evaluate the same expression, so what a locus keeps resident - and with it the order of every sum - does not
 // depend on which other loci share its launch: results are invariant under any partition of the loci over devices.
-constexpr size_t CL_SMEM_CAP = 200 * 1024;   // dynamic shared memory a CTA asks for at most (227 KB usable)
-__host__ __device__ inline size_t cluster_class_smem(int max_iso, size_t slice_bytes, int nt) {
-   const size_t fixed = cluster_fixed_doubles(max_iso) * sizeof(double);
+__host__ __device__ inline size_t cluster_class_smem(int max_iso, size_t slice_bytes, int nt, int cs) {
+   const size_t fixed = cluster_fixed_doubles(max_iso, cs, slice_bytes) * sizeof(double);
    const size_t stream = (size_t)(nt / CL_LPR_STREAM) * max_iso * sizeof(double);
    const size_t want = fixed + (slice_bytes > stream ? slice_bytes : stream) + 256;
    return want < CL_SMEM_CAP ? want : CL_SMEM_CAP;
@@ -802,6 +817,11 @@ __device__ __forceinline__ void slot_col_pass(const ResidentSlice& S, const ColS
    if (cs.j >= 0 && cs.q == 0) *cs.out = scale ? scale[cs.j] * sum : sum;
 }
 
+// split cluster barrier (all threads of every CTA execute them, convergently)
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
 // Where the partial theta'_j of this CTA goes: column j is owned by CTA j / B of the cluster, which keeps one
 // row of B partials per peer in its exchange area (written through distributed shared memory).
 struct OwnerMap {
@@ -843,16 +863,17 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
    double* bufA = th + T;              // [T] theta (current / next, swapped by pointer)
    double* bufB = bufA + T;            // [T]
    double* sdiv = bufB + T;            // [T] column sums s_j of the kept rows
-   double* part = sdiv + T;            // [2T+64] exchange area: stage [CS][B] of partial theta', dsq [B], flags [16], d2p [16]
-   double* dyn = part + 2 * T + 64;    // resident slice, or the streaming accumulators
+   double* part = sdiv + T;            // exchange area: stage [CS][B] of partial theta', dsq [B], flags [16], d2p [16] - or [CS][T] + 64 (all-to-all)
+   const int64_t* __restrict__ rp = p.row_ptr + r0;
+   const size_t slice_est = cluster_slice_estimate((long long)(rp[R] - rp[0]), R, T, (int)CS);
+   double* dyn = smem + cluster_fixed_doubles(T, (int)CS, slice_est);    // resident slice, or the streaming accumulators
    __shared__ double red[NT / 32];
    __shared__ int s_rows[2];
    double* cur = bufA;
    double* nxt = bufB;
 
-   const int64_t* __restrict__ rp = p.row_ptr + r0;
    // this locus' own shared-memory budget (<= what the launch provides: the class maximum of the same expression)
-   const unsigned smem_bytes = min(smem_launch, (unsigned)cluster_class_smem(T, cluster_slice_estimate((long long)(rp[R] - rp[0]), R, T, (int)CS), NT));
+   const unsigned smem_bytes = min(smem_launch, (unsigned)cluster_class_smem(T, slice_est, NT, (int)CS));
 
    // rows of this CTA: split by non-zeros (lower_bound on row_ptr)
    if (tid < 2) {
@@ -898,7 +919,7 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
    else if (resident) S.n_ent_s = (unsigned)min((size_t)nnz_c, (smem_bytes - used - cluster_resident_csr_bytes(nnz_c, (size_t)nrows, T)) / 4);
    S.nrows = nrows; S.T = T; S.nnz = nnz_c; S.npos = npos;
    GlobalRows grows{rp + ra, p.alpha + k_a, p.col + k_a, p.neff + r0 + ra, k_a};
-   const int G = resident ? 0 : cluster_stream_groups(T, smem_bytes, NT);
+   const int G = resident ? 0 : cluster_stream_groups(T, smem_bytes, NT, (int)CS, slice_est);
    double* acc = dyn;                                           // [G][T] (streaming only)
    const int g32 = tid / CL_LPR_STREAM, lg32 = tid % CL_LPR_STREAM;
    double* my_acc = acc + (size_t)(g32 < G ? g32 : 0) * T;
@@ -1204,14 +1225,18 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
 #endif
    // ---- exchange area: column j belongs to CTA j / B; every CTA pushes its partial theta'_j to the owner, the owner
    //      adds the CS partials in a fixed shape and pushes theta'_j and theta'_j / s_j back to everyone
-   const int B = (T + (int)CS - 1) / (int)CS;
-   double* stage = part;                       // [CS][B]
-   double* dsq = part + T + 16;                // [B] squared changes of the owned columns
-   double* flags = part + 2 * T + 32;          // [CS] zero-denominator flag of every CTA
+   const bool a2a = cluster_a2a(T, (int)CS, slice_est);
+   const int Tp = cluster_a2a_stride(T);
+   const int B = a2a ? Tp : (T + (int)CS - 1) / (int)CS;
+   double* stage = part;                       // [CS][B]; all-to-all: [CS][Tp], row r = the partials of CTA r
+   double* dsq = a2a ? part + (size_t)CS * Tp : part + T + 16;            // [B] squared changes of the owned columns ([NT / 32] per-warp sums)
+   double* flags = a2a ? dsq + 16 : part + 2 * T + 32;                    // [CS] zero-denominator flag of every CTA
    double* d2p = flags + 16;                   // [CS] partial ||theta' - theta||^2 of every owner
-   const OwnerMap own{&cluster, stage, B, rank, CS};
+   // all-to-all: the passes write this CTA's own row; owner form: column j goes to CTA j / B
+   const OwnerMap own{&cluster, a2a ? stage + (size_t)rank * Tp : stage, a2a ? T : B, a2a ? 0u : rank, a2a ? 1u : CS};
    if (slot.j >= 0) slot.out = own.ptr(slot.j);
    const int nb = max(0, min(B, T - (int)rank * B));      // columns this CTA owns
+   bool pend_b = false;                        // all-to-all: arrived at the "stage has been read" barrier, not yet waited
    if (kept_all == 0) {
       status = LOCUS_NO_ROWS;
    } else {
@@ -1258,6 +1283,52 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
             SBQ_TICK(6)
 #pragma unroll
             for (int w = 0; w < NT / 32; ++w) d2 += dsq[w];      // same order in every thread
+         } else if (a2a) {
+            __syncthreads();                                     // this CTA's row of partials is complete
+            if (pend_b) { cluster_wait(); pend_b = false; }      // every peer has finished reading the previous iteration's rows
+            {
+               // broadcast the row (and the zero-denominator flag) to the CS - 1 peers: coalesced 16-byte remote stores
+               const int half = Tp >> 1, items = ((int)CS - 1) * half;
+               const double2* mine = reinterpret_cast<const double2*>(stage + (size_t)rank * Tp);
+               for (int x = tid; x < items; x += NT) {
+                  const int pr = x / half, jj = x - pr * half;
+                  const unsigned peer = (rank + 1u + (unsigned)pr) & (CS - 1u);
+                  reinterpret_cast<double2*>(cluster.map_shared_rank(stage, peer) + (size_t)rank * Tp)[jj] = mine[jj];
+               }
+               if (tid < (int)CS) cluster.map_shared_rank(flags, (unsigned)tid)[rank] = (double)zero;
+            }
+            SBQ_TICK(3)
+            cluster_arrive_release();
+            cluster_wait();
+            SBQ_TICK(4)
+            double zf = 0.0;
+            for (unsigned r = 0; r < CS; ++r) zf += flags[r];
+            if (zf != 0.0) { status = LOCUS_ZERO_DENOM; break; }
+            // every CTA adds the CS rows itself, in the shape of a butterfly over CS lanes (the association of the owner form)
+            double dd = 0.0;
+            for (int j = tid; j < T; j += NT) {
+               double a[16];
+#pragma unroll
+               for (int r = 0; r < 16; ++r) a[r] = r < (int)CS ? stage[(size_t)r * Tp + j] : 0.0;
+#pragma unroll
+               for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+                  for (int r = 0; r < o; ++r) a[r] += a[r + o];
+               const double v = a[0], sj = sdiv[j];
+               nxt[j] = v;
+               th[j] = (sj != 0) ? v / sj : 0.0;
+               const double diff = v - cur[j];
+               dd += diff * diff;
+            }
+            if ((tid & ~31) < T) dd = warp_sum(dd);              // warps without columns hold 0 already
+            if (lane == 0) dsq[tid >> 5] = dd;
+            SBQ_TICK(5)
+            __syncthreads();
+            cluster_arrive_relaxed();                            // done reading the rows and the flags (waited for before the next broadcast)
+            pend_b = true;
+            SBQ_TICK(6)
+#pragma unroll
+            for (int w = 0; w < NT / 32; ++w) d2 += dsq[w];      // same order in every thread of every CTA
          } else {
             if (tid < (int)CS) cluster.map_shared_rank(flags, (unsigned)tid)[rank] = (double)zero;
             cluster.sync();
@@ -1309,6 +1380,7 @@ em_cluster_kernel(DevParams p, const int32_t* __restrict__ list, int n_list, uns
       printf("locus %d tid %d iters %d resident %d csc_smem %d slots %d/%d lanes %d/%d ncache %d lpr %d lpc %d nrows %d nnz %u setup %lld | E %lld or %lld col %lld csync1 %lld own %lld d2 %lld csync2 %lld chk %lld (cycles/iter)\n", l, tid, iters,
              (int)resident, (int)csc_in_smem, (int)use_row_slots, (int)use_slots, rslot.lanes, slot.lanes, slot.ncache, lpr, lpc, nrows, nnz_c, t_setup, ph[0] / iters, ph[1] / iters, ph[2] / iters, ph[3] / iters, ph[4] / iters, ph[5] / iters, ph[6] / iters, ph[7] / iters);
 #endif
+   if (pend_b) cluster_wait();
    cluster.sync();   // no CTA may exit while a peer can still read its shared memory
 #ifdef SBQ_TRACE
    if (tid == 0) trace_emit(CS, NT, l, rank, trace_t0, iters);

@@ -320,6 +320,18 @@ def test_grid_tier_two_slot_layout_edge_shapes(q, oracle_mod, monkeypatch):
     assert np.array_equal(res["theta"], again["theta"]) and np.array_equal(res["iters"], again["iters"])
 
 
+@pytest.mark.parametrize("T", [1400, 2000])
+def test_grid_tier_two_slot_wide_loci(q, oracle_mod, monkeypatch, T):
+    """Loci wider than T = 1300 run the two-slot kernel with 6 / 4 warps per CTA (by default since round 2: faster than the
+    TMA ring kernel there): same edge-shape locus as above, layout verified, against the oracle."""
+    b = _two_slot_edge_locus(9001, T, 31)
+    ora = oracle_mod.quantify_batch(b, b["total_mapped_reads"], n_threads=2)
+    monkeypatch.setenv("SBQ_DUAL_VERIFY", "1")
+    res = run_gpu(q, b, 3, 0)
+    assert [r["kernel"] for r in q.launch_stats() if r["n_loci"]] == ["em_grid_dual_kernel"]
+    assert_matches_oracle(res, ora, b, "two-slot grid kernel, T = %d" % T)
+
+
 def test_grid_tier_two_slot_rows_with_unsorted_columns(q, oracle_mod, monkeypatch):
     """The two-slot layout pairs rows by merging their (ascending) column lists; a row whose columns are not strictly
     ascending (out of contract: sbq_validate rejects it, but validation is optional) must stay in CSR order and be walked

@@ -1,5 +1,5 @@
 """Small profiling driver (run under ncu on the GPU box):
-   python tools/prof.py giant [rows] [max_iter]   one giant locus through the grid tier
+   python tools/prof.py giant [rows] [max_iter] [iso_lo iso_hi]   one giant locus through the grid tier
    python tools/prof.py human [n_loci]            human-shaped batch through all tiers
 """
 import os
@@ -13,7 +13,8 @@ mode = sys.argv[1] if len(sys.argv) > 1 else "giant"
 if mode == "giant":
     rows = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
     max_iter = int(sys.argv[3]) if len(sys.argv) > 3 else 8
-    b = synth.giant(n_loci=1, rows_per_locus=rows, seed=4)
+    iso = (int(sys.argv[4]), int(sys.argv[5])) if len(sys.argv) > 5 else (500, 800)     # optional: T range
+    b = synth.giant(n_loci=1, rows_per_locus=rows, seed=4, iso_lo=iso[0], iso_hi=iso[1])
     q = api.Quantifier(max_iter=max_iter)
 else:
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
