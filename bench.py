@@ -439,8 +439,8 @@ def bias_leg(args, api, partition, synth, local_rank, rank, world, flush, reduce
            "workload": "configs[2]: the seed-2 batch (20000 loci, 10M fragments) with 5 per-row covariates (gc, gc^2, gc^3, log bin length, mean fragment length; seed 3), "
                        f"bias-corrected EM, LPT over {world} GPU(s)",
            "value": fi / (ms_max * 1e-3), "unit": UNIT, "ms_per_step": ms_max, "theta_iters_total": int(it_all), "outer_rounds_total": int(outer_all),
-           "kernel": "em_bias_kernel (one 256-thread CTA per locus, rows streamed from L2: no size tiers yet - the largest loci bound the step)",
-           "gpu_launches": int(launches * 2)}
+           "kernel": "em_bias_warp_kernel (small loci: one warp per locus, persistent warps) + em_bias_kernel (one cluster of 1 / 2 / 4 / 8 / 16 CTAs per locus by non-zeros, rows streamed from L2, partial sums exchanged through distributed shared memory)",
+           "gpu_launches": int(launches * 3)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
         rng = np.random.default_rng(7)

@@ -100,6 +100,11 @@ struct LaunchClass {      // one kernel launch of the cluster tier
    size_t smem = 0;
 };
 
+struct BiasClass {        // one launch of the bias kernel: the loci of one cluster size
+   int cs = 1, max_iso = 1;
+   size_t off = 0, n = 0;
+};
+
 struct LaunchTimer {      // CUDA events around one kernel launch, on the stream it is launched on
    cudaEvent_t e0 = nullptr, e1 = nullptr;
    bool used = false;
@@ -150,6 +155,10 @@ struct sbq_ctx {
    int n_cov = 0;
    bool have_cov = false;
    DevBuf d_bias;
+   int32_t* d_bias_list = nullptr;          // loci grouped by the cluster size of the bias kernel (inside d_bias)
+   std::vector<int32_t> bias_list;
+   BiasClass bias_cls[6];                   // cluster sizes 16, 8, 4, 2, 1 and the warp tier
+   int* d_bias_queue = nullptr;             // work queue of the persistent warps of em_bias_warp_kernel
    BiasParams bpar{};
    PinnedVec<double> r_beta;
    PinnedVec<int32_t> r_outer;
@@ -1011,14 +1020,37 @@ int sbq_upload(sbq_ctx* c) {
       if (!c->have_cov) return fail(c, SBQ_ERR_STATE, "bias_mode = 1 needs sbq_set_covariates() after the last submit");
       const size_t K = (size_t)c->n_cov;
       const size_t bx = align_up(c->n_row * K * 8 + 8), bw = align_up(c->n_row * 8 + 8), bb = align_up(c->n_loci * K * 8 + 8), bo = align_up(c->n_loci * 4 + 8);
-      if (!c->d_bias.reserve(bx + 2 * bw + bb + bo)) return fail(c, SBQ_ERR_NOMEM, "device allocation failed (bias scratch)");
+      if (!c->d_bias.reserve(bx + 2 * bw + bb + 2 * bo + 64)) return fail(c, SBQ_ERR_NOMEM, "device allocation failed (bias scratch)");
       char* q = (char*)c->d_bias.p;
       c->bpar.x = (const double*)q; q += bx;
       c->bpar.w = (double*)q; q += bw;
       c->bpar.d = (double*)q; q += bw;
       c->bpar.beta = (double*)q; q += bb;
-      c->bpar.outer = (int32_t*)q;
+      c->bpar.outer = (int32_t*)q; q += bo;
+      c->d_bias_list = (int32_t*)q; q += bo;
+      c->d_bias_queue = (int*)q;
       c->bpar.n_cov = c->n_cov;
+      // launch classes of the bias kernel: cluster size by non-zeros (a function of the locus alone), biggest loci first
+      {
+         c->bias_list.clear();
+         std::vector<int32_t> cls[6];
+         for (int k = 0; k < 6; ++k) c->bias_cls[k] = BiasClass{};
+         for (int64_t l = 0; l < c->n_loci; ++l) {
+            const int cs = bias_cluster_size(c->meta[l].nnz);
+            // class 5: small loci, one warp each (em_bias_warp_kernel)
+            const int k = bias_warp_tier(c->meta[l].nnz, c->meta[l].R, c->meta[l].T) ? 5 : cs == 16 ? 0 : cs == 8 ? 1 : cs == 4 ? 2 : cs == 2 ? 3 : 4;
+            cls[k].push_back((int32_t)l);
+            c->bias_cls[k].cs = cs;
+            c->bias_cls[k].max_iso = std::max(c->bias_cls[k].max_iso, (int)c->meta[l].T);
+         }
+         for (int k = 0; k < 6; ++k) {
+            std::sort(cls[k].begin(), cls[k].end(), [&](int32_t a, int32_t b) { return c->meta[a].nnz != c->meta[b].nnz ? c->meta[a].nnz > c->meta[b].nnz : a < b; });
+            c->bias_cls[k].off = c->bias_list.size();
+            c->bias_cls[k].n = cls[k].size();
+            c->bias_list.insert(c->bias_list.end(), cls[k].begin(), cls[k].end());
+         }
+         if (c->n_loci) CU(cudaMemcpyAsync(c->d_bias_list, c->bias_list.data(), c->n_loci * 4, cudaMemcpyHostToDevice, c->stream));
+      }
       if (K) CU(cudaMemcpyAsync((void*)c->bpar.x, c->h_cov.p, c->n_row * K * 8, cudaMemcpyHostToDevice, c->stream));
       CU(cudaStreamSynchronize(c->stream));
       c->stats.h2d_bytes += (int64_t)(c->n_row * K * 8);
@@ -1048,17 +1080,61 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
    cudaStream_t st = c->stream;
    int64_t launches = 0;
    if (c->cfg.bias_mode == 1) {
-      // bias-corrected EM: one fused kernel (theta-EM + bias-weight update + both convergence tests), one CTA per locus
+      // bias-corrected EM: one fused kernel (theta-EM + bias-weight update + both convergence tests), one cluster of 1 - 16 CTAs
+      // per locus; one launch per cluster size, concurrently on the side streams, the biggest clusters first
       const size_t smem = bias_smem_bytes(c->max_iso_all);
-      if (smem > SMEM_CAP) return fail(c, SBQ_ERR_UNSUPPORTED, "bias mode supports up to %d isoforms per locus", (int)(SMEM_CAP / (8 * (4 + BI_W))));
+      if (smem > SMEM_CAP) return fail(c, SBQ_ERR_UNSUPPORTED, "bias mode supports up to %d isoforms per locus", (int)((SMEM_CAP / 8 - 8) / (5 + BI_W)));
       c->bpar.max_out_it = c->cfg.max_out_it;
       c->bpar.max_theta_it = c->cfg.max_theta_it;
       c->bpar.max_bias_it = c->cfg.max_bias_it;
       c->bpar.bias_tol = c->cfg.bias_tol;
-      CU(cudaFuncSetAttribute(em_bias_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int rc_attr = set_kernel_attrs(c, em_bias_kernel, smem, c->bias_cls[0].n > 0);
+      if (rc_attr) return rc_attr;
       CU(cudaEventRecord(c->ev[2], st));
-      em_bias_kernel<<<(unsigned)c->n_loci, BI_NT, smem, st>>>(c->dp, c->bpar, (int)c->n_loci);
-      CU(cudaGetLastError());
+      CU(cudaEventRecord(c->ev_fork, st));
+      int n_side = 0;
+      if (c->bias_cls[5].n) {
+         // small loci: persistent warps, one locus per warp at a time (longest first); runs beside the cluster launches
+         const BiasClass& bc = c->bias_cls[5];
+         cudaStream_t ss = c->side[n_side];
+         CU(cudaStreamWaitEvent(ss, c->ev_fork, 0));
+         ++n_side;
+         const size_t wsmem = bias_warp_smem_bytes();
+         CU(cudaFuncSetAttribute(em_bias_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+         int occ = 1;
+         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, em_bias_warp_kernel, BW_WARPS * 32, wsmem));
+         const long long want = ((long long)bc.n + BW_WARPS - 1) / BW_WARPS;
+         const unsigned grid = (unsigned)std::max(1LL, std::min(want, (long long)c->prop.multiProcessorCount * std::max(1, occ)));
+         CU(cudaMemsetAsync(c->d_bias_queue, 0, sizeof(int), ss));
+         em_bias_warp_kernel<<<grid, BW_WARPS * 32, wsmem, ss>>>(c->dp, c->bpar, (const int32_t*)(c->d_bias_list + bc.off), (int)bc.n, c->d_bias_queue);
+         CU(cudaGetLastError());
+         ++launches;
+      }
+      for (int k = 0; k < 5; ++k) {
+         const BiasClass& bc = c->bias_cls[k];
+         if (!bc.n) continue;
+         cudaStream_t ss = c->side[n_side % N_SIDE_STREAMS];
+         if (n_side < N_SIDE_STREAMS) CU(cudaStreamWaitEvent(ss, c->ev_fork, 0));
+         ++n_side;
+         cudaLaunchConfig_t cfg{};
+         cfg.gridDim = dim3((unsigned)(bc.n * bc.cs));
+         cfg.blockDim = dim3(BI_NT);
+         cfg.dynamicSmemBytes = bias_smem_bytes(bc.max_iso);
+         cfg.stream = ss;
+         cudaLaunchAttribute attr[1];
+         attr[0].id = cudaLaunchAttributeClusterDimension;
+         attr[0].val.clusterDim.x = (unsigned)bc.cs;
+         attr[0].val.clusterDim.y = 1;
+         attr[0].val.clusterDim.z = 1;
+         cfg.attrs = attr;
+         cfg.numAttrs = 1;
+         CU(cudaLaunchKernelEx(&cfg, em_bias_kernel, c->dp, c->bpar, (const int32_t*)(c->d_bias_list + bc.off), (int)bc.n));
+         ++launches;
+      }
+      for (int i = 0; i < std::min(n_side, N_SIDE_STREAMS); ++i) {
+         CU(cudaEventRecord(c->ev_join[i], c->side[i]));
+         CU(cudaStreamWaitEvent(st, c->ev_join[i], 0));
+      }
       CU(cudaEventRecord(c->ev[3], st));
       fpkm_sum_kernel<<<1, 1024, 0, st>>>(dp.locus_fpkm, c->n_loci, c->d_fpkm_sum);
       CU(cudaGetLastError());
@@ -1070,7 +1146,7 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
       CU(cudaEventElapsedTime(&ms_, c->ev[2], c->ev[3]));
       c->stats.em_ms = ms_;
       c->stats.grid_em_ms = 0;
-      c->stats.kernel_launches = 2;
+      c->stats.kernel_launches = launches + 1;
       c->launch_stats.clear();
       c->locus_launch.assign(c->n_loci, -1);
       c->solved = true;

@@ -50,7 +50,9 @@ def test_restatement_recovers_a_planted_bias_direction(oracle_mod):
 @pytest.mark.gpu
 def test_bias_kernel_matches_restatement(oracle_mod, sbq_lib_path):
     from strawberry_b200 import api
-    loci = [biased_locus(s, T=int(t), R=int(r), K=k) for s, t, r, k in ((3, 4, 60, 5), (4, 12, 300, 5), (5, 40, 900, 3), (6, 3, 20, 2), (7, 8, 150, 0))]
+    loci = [biased_locus(s, T=int(t), R=int(r), K=k) for s, t, r, k in ((3, 4, 60, 5), (4, 12, 300, 5), (5, 40, 900, 3), (6, 3, 20, 2), (7, 8, 150, 0),
+                                                                                # loci large enough for clusters of 2, 8 and 16 CTAs (non-zeros > 6 k / 40 k / 100 k)
+                                                                                (8, 30, 700, 3), (9, 60, 2000, 5), (10, 80, 3000, 2))]
     for K in sorted({l["X"].shape[1] for l in loci}):
         group = [l for l in loci if l["X"].shape[1] == K]
         parts = [dict(loc_row_off=np.array([0, len(l["count"])]), loc_iso_off=np.array([0, l["T"]]), row_ptr=l["row_ptr"], col=l["col"],
