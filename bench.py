@@ -142,7 +142,7 @@ def reference_arm(args, rank, world):
     ms = 1e3 * float(np.mean(secs))
     value = frag_iters / (ms / 1e3)
     sample = (f"the full workload per step: 20000 loci, {frag_iters} fragment-iters; "
-              f"{'reference EmSolver::init/run (dense Eigen, src/estimate.cpp:366-488), one std::thread per core over loci' if use_ref else 'C port of the reference EM, pthreads'}")
+              f"{'reference EmSolver::init/run (dense Eigen, src/estimate.cpp:366-488), one std::thread per core pulling loci largest first (dense cost R x T)' if use_ref else 'C port of the reference EM, pthreads'}")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",

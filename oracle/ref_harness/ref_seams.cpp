@@ -19,6 +19,7 @@
 #include <string>
 #include <sstream>
 #include <thread>
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <vector>
@@ -79,11 +80,22 @@ int ref_em_solve(int T, int R, const int* n, const double* alpha, double* theta_
 double ref_em_solve_batch(long n_loci, const long* loc_row_off, const long* loc_iso_off,
                           const long* row_ptr, const int* col, const double* alpha, const int* count,
                           double* theta_out, int* rc_out, int n_threads) {
+   // Loci are handed out largest first (dense cost R x T, what EmSolver works on): with the natural order a big locus picked
+   // up late leaves the other threads idle at the end. The sort is outside the timed region - the most favourable
+   // schedule a thread pool over independent loci can get.
+   std::vector<long> order(n_loci);
+   for (long l = 0; l < n_loci; ++l) order[l] = l;
+   std::stable_sort(order.begin(), order.end(), [&](long a, long b) {
+      const long ca = (loc_row_off[a + 1] - loc_row_off[a]) * (loc_iso_off[a + 1] - loc_iso_off[a]);
+      const long cb = (loc_row_off[b + 1] - loc_row_off[b]) * (loc_iso_off[b + 1] - loc_iso_off[b]);
+      return ca > cb;
+   });
    std::atomic<long> next(0);
    auto work = [&]() {
       for (;;) {
-         long l = next.fetch_add(1);
-         if (l >= n_loci) break;
+         const long w = next.fetch_add(1);
+         if (w >= n_loci) break;
+         const long l = order[w];
          long r0 = loc_row_off[l], r1 = loc_row_off[l + 1];
          long t0 = loc_iso_off[l], T = loc_iso_off[l + 1] - t0;
          long R = r1 - r0;
