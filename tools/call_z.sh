@@ -1,3 +1,6 @@
 #!/bin/bash
-timeout 600 python -m pytest tests/test_bias.py -x -q -m gpu 2>&1 | tail -15
-timeout 900 python tools/bias_profile.py 2>&1 | tail -24
+mkdir -p gpurun_out
+for tool in racecheck synccheck memcheck; do
+  timeout 1200 compute-sanitizer --tool $tool python tools/sanitize.py > gpurun_out/r02z_sanitize_$tool.log 2>&1
+  grep -E "ok|SUMMARY|ERROR" gpurun_out/r02z_sanitize_$tool.log | tail -12
+done

@@ -1,6 +1,7 @@
 """Small all-tier workload for compute-sanitizer (memcheck / racecheck / synccheck): warp tier, cluster tier with cluster
-sizes 1 / 4 / 16 (64-, 128- and 512-thread CTAs), grid tier (two-slot kernel incl. its layout and packing passes, TMA ring
-kernel), the on-device generator, the device class-table builder and the GPU class weights."""
+sizes 1 / 4 / 16 (64-, 128- and 512-thread CTAs; all-to-all and owner exchange), grid tier (two-slot kernel incl. its layout and
+packing passes, TMA ring kernel), the bias kernels (warp tier and clusters of 1 - 16 CTAs), the on-device generator, the device
+class-table builder and the GPU class weights."""
 import os
 import sys
 
@@ -29,6 +30,13 @@ for tier, cs, it in ((0, 0, 30), (2, 1, 10), (2, 4, 10), (2, 16, 10), (3, 0, 6))
     r = q.results()
     print("tier", tier, "cs", cs, "ok", np.isfinite(r["theta"]).all(), q.stats()["kernel_launches"])
     q.close()
+q = api.Quantifier(bias_mode=1, max_out_it=2, max_theta_it=4, max_bias_it=2)     # bias kernels: warp tier + clusters of 1 .. 16 CTAs
+bb = synth.concat([b] + [synth.giant(n_loci=1, rows_per_locus=r, seed=4) for r in (200, 600, 1500)])     # + 9.6 k / 29 k / 72 k non-zeros: clusters of 2, 4, 8
+q.submit_flat(bb)
+q.set_covariates(synth.covariates(bb, seed=3))
+q.run(bb["total_mapped_reads"])
+print("bias ok", np.isfinite(q.results()["theta"]).all(), q.stats()["kernel_launches"])
+q.close()
 os.environ["SBQ_GRID_NO_DUAL"] = "1"                      # the TMA ring kernel
 q = api.Quantifier(max_iter=4)
 q.set_plan(3, 0)
