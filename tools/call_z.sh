@@ -1,6 +1,3 @@
 #!/bin/bash
-mkdir -p gpurun_out
-for tool in racecheck synccheck memcheck; do
-  timeout 1200 compute-sanitizer --tool $tool python tools/sanitize.py > gpurun_out/r02z_sanitize_$tool.log 2>&1
-  grep -E "ok|SUMMARY|ERROR" gpurun_out/r02z_sanitize_$tool.log | tail -12
-done
+SBQ_LIB_PATH=build/variants/libsbq_nofence.so timeout 300 python tools/prof.py giant 1000000 40 2>&1 | grep -E "grid GB"
+SBQ_LIB_PATH=build/variants/libsbq_phases.so timeout 300 python tools/prof.py giant 1000000 40 2>&1 | grep -E "G6PHASES|grid GB" | tail -2
