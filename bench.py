@@ -496,6 +496,13 @@ def giant_leg(args, api, partition, synth, local_rank, rank, world, flush, reduc
     fpkm_local = 0.0
     kernel = "em_grid_kernel"
     wave_ms_per_pass = []
+    # untimed warm-up at FULL wave size: the first full-size solve allocates the layout buffers of the grid tier (packed chunk stream,
+    # row records, 16-bit slots: ~ 12 GB for 25 loci) between the timing events - seen to cost up to 1 s on a fresh box
+    if waves:
+        qg.clear()
+        qg.synth_giant(waves[0], rows, seed=seed)
+        qg.solve(rows * n)
+        barrier()
     clk = ClockSampler(local_rank)
     clk.__enter__()
     t0 = time.perf_counter()
