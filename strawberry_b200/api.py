@@ -189,6 +189,7 @@ class Quantifier:
 
     def close(self):
         self._fin()
+        self._h = None          # a call on a closed Quantifier raises (ctypes passes NULL -> SBQ_ERR_INVALID) instead of touching freed memory
 
     def _chk(self, rc):
         if rc < 0:

@@ -203,6 +203,18 @@ struct sbq_ctx {
    // device
    DevBuf d_in, d_out, d_lists, d_grid_scratch, d_col16, d_rowrec, d_csc, d_synth, d_pk;
    bool col16_ready = false, grid_tma_ok = false, grid_dual_ok = false;
+   // "Small giants" (grid-tier loci below SGRID_MAX_NNZ non-zeros, a few thousand rows): the same grid kernels on a SUB-GRID of
+   // SGRID_CTAS CTAs, on a stream of their own, so that the cluster and warp tiers keep the other SMs (the full-grid launch of a
+   // 400 k-non-zero locus idles most of the GPU for milliseconds: its iterations are barrier latency, not bandwidth).
+   std::vector<int32_t> sgrid_list;
+   std::vector<int64_t> sgrid_rec_off;
+   size_t sgrid_list_off = 0, sgrid_n_dual = 0;
+   int sgrid_max_iso = 1, sgrid_max_iso_dual = 1, sgrid_variant = 0;
+   bool sgrid_tma_ok = false;
+   DevBuf d_sgrid_scratch, d_srowrec, d_spk;
+   cudaStream_t sgrid_st = nullptr;
+   cudaEvent_t ev_sgrid_join = nullptr;
+   LaunchTimer lt_sgrid;
    std::vector<int64_t> grid_rec_off;            // row-record offset of every two-slot-kernel locus (+ total), list order
    size_t grid_n_dual = 0;                       // the first grid_n_dual entries of grid_list run on the two-slot kernel, the rest on the TMA ring / register-staged kernel
    int grid_max_iso_dual = 1;
@@ -317,6 +329,9 @@ constexpr int N_BUCKETS = 5;
 const int BUCKET_NT[N_BUCKETS] = {64, 128, 512, 512, 512};
 int smem_bucket(size_t bytes) { return bytes <= 12 * 1024 ? 0 : bytes <= 24 * 1024 ? 1 : bytes <= 56 * 1024 ? 2 : bytes <= 112 * 1024 ? 3 : 4; }
 
+constexpr int64_t SGRID_MAX_NNZ = 4 * 1000 * 1000;   // grid-tier loci below this run on a sub-grid ...
+constexpr int SGRID_CTAS = 32;                       // ... of this many CTAs (one per SM), beside the other tiers
+
 int cluster_size_for(int64_t nnz) {
    // ~14 B of shared memory per non-zero (row part + CSC index): a CTA's slice stays under ~14k non-zeros, which still
    // fits with its CSC index. Smaller clusters cost latency per iteration (fewer SMs per locus) but less SM time in
@@ -352,6 +367,9 @@ void capture_meta_host(sbq_ctx* c) {
 int plan(sbq_ctx* c) {
    c->warp_list.clear();
    c->grid_list.clear();
+   c->sgrid_list.clear();
+   c->sgrid_max_iso = c->sgrid_max_iso_dual = 1;
+   c->sgrid_tma_ok = true;
    c->classes.clear();
    c->warp_max_iso = 1;
    c->max_iso_all = 1;
@@ -360,12 +378,14 @@ int plan(sbq_ctx* c) {
    c->grid_tma_ok = true;
    c->grid_dual_ok = !getenv("SBQ_GRID_NO_DUAL");   // two-slot layout kernel (sbq_grid_dual.cuh) for the loci that qualify
    const bool force_dual = getenv("SBQ_GRID_DUAL") != nullptr;
+   static const bool sgrid_enabled = !getenv("SBQ_NO_SGRID");   // tuning aid: every grid-tier locus on the full grid
    std::vector<char> dual_locus(c->n_loci, 0);
    std::vector<int64_t> nnz_of(c->n_loci);
    LaunchClass* slot[5][N_BUCKETS] = {};
    std::vector<LaunchClass> tmp;
    tmp.reserve(20);
-   const int64_t grid_min_nnz = 300 * 1000;   // above this a locus is faster on the whole GPU than on a 16-CTA cluster
+   // above this a locus goes to the grid tier (SBQ_GRID_MIN_NNZ overrides: tuning aid)
+   static const int64_t grid_min_nnz = getenv("SBQ_GRID_MIN_NNZ") ? atoll(getenv("SBQ_GRID_MIN_NNZ")) : 300 * 1000;
    for (int64_t l = 0; l < c->n_loci; ++l) {
       const int64_t R = c->meta[l].R, T = c->meta[l].T, nnz = c->meta[l].nnz;
       nnz_of[l] = nnz;
@@ -391,16 +411,21 @@ int plan(sbq_ctx* c) {
          c->warp_list.push_back((int32_t)l);
          c->warp_max_iso = std::max(c->warp_max_iso, (int)T);
       } else if (tier == 3) {
-         c->grid_list.push_back((int32_t)l);
+         // sub-grid class: a function of the locus alone (a forced tier - tests, tools - keeps the full grid)
+         const bool small = !c->force_tier && sgrid_enabled && nnz < SGRID_MAX_NNZ;
+         (small ? c->sgrid_list : c->grid_list).push_back((int32_t)l);
          // bank-aligned two-slot layout: 16-bit slot offsets, 32-bit offsets inside the locus, rows short enough on average
          const bool dual = c->grid_dual_ok && (grid_dual_supports_iso((int)T) || (force_dual && grid_dual_possible((int)T))) &&
                            nnz < (1LL << 32) && nnz <= 56 * R;
          dual_locus[l] = dual;
+         int& mx_dual = small ? c->sgrid_max_iso_dual : c->grid_max_iso_dual;
+         int& mx_rest = small ? c->sgrid_max_iso : c->grid_max_iso;
+         bool& tma_ok = small ? c->sgrid_tma_ok : c->grid_tma_ok;
          if (dual) {
-            c->grid_max_iso_dual = std::max(c->grid_max_iso_dual, (int)T);
+            mx_dual = std::max(mx_dual, (int)T);
          } else {
-            c->grid_max_iso = std::max(c->grid_max_iso, (int)T);
-            if (!grid_tma_supports((int)T, (long long)R, c->prop.multiProcessorCount)) c->grid_tma_ok = false;
+            mx_rest = std::max(mx_rest, (int)T);
+            if (!grid_tma_supports((int)T, (long long)R, small ? SGRID_CTAS : c->prop.multiProcessorCount)) tma_ok = false;
          }
       } else {
          int cs = c->force_cluster ? c->force_cluster : cluster_size_for(nnz);
@@ -438,20 +463,22 @@ int plan(sbq_ctx* c) {
    }
    // two-slot-kernel loci first, each part by descending size
    // (within the two-slot part: by the warp count the locus' own T allows, so that every launch group is homogeneous)
-   std::sort(c->grid_list.begin(), c->grid_list.end(), [&](int32_t a, int32_t b) {
-      if (dual_locus[a] != dual_locus[b]) return dual_locus[a] > dual_locus[b];
-      if (dual_locus[a]) {
-         const int na = grid_dual_nc(c->meta[a].T), nb_ = grid_dual_nc(c->meta[b].T);
-         if (na != nb_) return na > nb_;
-      }
-      return by_size(a, b);
-   });
-   c->grid_n_dual = 0;
-   for (int32_t l : c->grid_list) c->grid_n_dual += dual_locus[l];
-   c->grid_rec_off.assign(c->grid_n_dual + 1, 0);
-   for (size_t i = 0; i < c->grid_n_dual; ++i) {
-      c->grid_rec_off[i + 1] = c->grid_rec_off[i] + c->meta[c->grid_list[i]].R + 1;
-   }
+   auto order_grid = [&](std::vector<int32_t>& list, size_t& n_dual, std::vector<int64_t>& rec_off) {
+      std::sort(list.begin(), list.end(), [&](int32_t a, int32_t b) {
+         if (dual_locus[a] != dual_locus[b]) return dual_locus[a] > dual_locus[b];
+         if (dual_locus[a]) {
+            const int na = grid_dual_nc(c->meta[a].T), nb_ = grid_dual_nc(c->meta[b].T);
+            if (na != nb_) return na > nb_;
+         }
+         return by_size(a, b);
+      });
+      n_dual = 0;
+      for (int32_t l : list) n_dual += dual_locus[l];
+      rec_off.assign(n_dual + 1, 0);
+      for (size_t i = 0; i < n_dual; ++i) rec_off[i + 1] = rec_off[i] + c->meta[list[i]].R + 1;
+   };
+   order_grid(c->grid_list, c->grid_n_dual, c->grid_rec_off);
+   order_grid(c->sgrid_list, c->sgrid_n_dual, c->sgrid_rec_off);
    for (auto& lc : tmp) {
       std::sort(lc.loci.begin(), lc.loci.end(), by_size);
       if (cluster_stream_groups(lc.max_iso, SMEM_CAP, lc.lpr, 1, 0) <= 0)
@@ -466,12 +493,14 @@ int plan(sbq_ctx* c) {
    if (!c->h_lists.append(c->warp_list.data(), c->warp_list.size())) return fail(c, SBQ_ERR_NOMEM, "list staging");
    c->grid_list_off = c->h_lists.n;
    if (!c->h_lists.append(c->grid_list.data(), c->grid_list.size())) return fail(c, SBQ_ERR_NOMEM, "list staging");
+   c->sgrid_list_off = c->h_lists.n;
+   if (!c->h_lists.append(c->sgrid_list.data(), c->sgrid_list.size())) return fail(c, SBQ_ERR_NOMEM, "list staging");
    for (auto& lc : c->classes) {
       lc.list_off = c->h_lists.n;
       if (!c->h_lists.append(lc.loci.data(), lc.loci.size())) return fail(c, SBQ_ERR_NOMEM, "list staging");
    }
    c->stats.loci_warp = (int64_t)c->warp_list.size();
-   c->stats.loci_grid = (int64_t)c->grid_list.size();
+   c->stats.loci_grid = (int64_t)(c->grid_list.size() + c->sgrid_list.size());
    c->stats.loci_cta = c->n_loci - c->stats.loci_warp - c->stats.loci_grid;
    return SBQ_SUCCESS;
 }
@@ -691,6 +720,9 @@ int sbq_create(const sbq_config* cfg, sbq_ctx** out) {
       if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(SBQ_ERR_CUDA);
    for (auto& t : c->lt)
       if (cudaEventCreate(&t.e0) != cudaSuccess || cudaEventCreate(&t.e1) != cudaSuccess) return bail(SBQ_ERR_CUDA);
+   if (cudaStreamCreateWithFlags(&c->sgrid_st, cudaStreamNonBlocking) != cudaSuccess) return bail(SBQ_ERR_CUDA);
+   if (cudaEventCreateWithFlags(&c->ev_sgrid_join, cudaEventDisableTiming) != cudaSuccess) return bail(SBQ_ERR_CUDA);
+   if (cudaEventCreate(&c->lt_sgrid.e0) != cudaSuccess || cudaEventCreate(&c->lt_sgrid.e1) != cudaSuccess) return bail(SBQ_ERR_CUDA);
    if (cfg->n_gpus > 1) {
       const int rc = multi_create(c, ndev);
       if (rc) {
@@ -714,6 +746,7 @@ void sbq_destroy(sbq_ctx* c) {
    c->r_theta.release(); c->r_fpkm.release(); c->r_frac.release(); c->r_tpm.release();
    c->r_locus_fpkm.release(); c->r_keep.release(); c->r_iters.release(); c->r_status.release(); c->r_frags.release(); c->d_frags.release();
    c->d_in.release(); c->d_out.release(); c->d_lists.release(); c->d_grid_scratch.release(); c->d_col16.release(); c->d_rowrec.release(); c->d_csc.release(); c->d_synth.release(); c->d_pk.release(); c->d_raw.release(); c->d_raw2.release(); c->d_bias.release();
+   c->d_sgrid_scratch.release(); c->d_srowrec.release(); c->d_spk.release();
    c->h_cov.release(); c->r_beta.release(); c->r_outer.release();
    c->h_wseg.release(); c->h_wn.release(); c->h_wmask.release(); c->h_wpool.release(); c->h_wlen.release(); c->h_wpool_off.release(); c->d_weights.release();
    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -721,6 +754,10 @@ void sbq_destroy(sbq_ctx* c) {
    for (auto& e : c->ev_join) if (e) cudaEventDestroy(e);
    for (auto& t : c->lt) { if (t.e0) cudaEventDestroy(t.e0); if (t.e1) cudaEventDestroy(t.e1); }
    for (auto& s : c->side) if (s) cudaStreamDestroy(s);
+   if (c->lt_sgrid.e0) cudaEventDestroy(c->lt_sgrid.e0);
+   if (c->lt_sgrid.e1) cudaEventDestroy(c->lt_sgrid.e1);
+   if (c->ev_sgrid_join) cudaEventDestroy(c->ev_sgrid_join);
+   if (c->sgrid_st) cudaStreamSynchronize(c->sgrid_st), cudaStreamDestroy(c->sgrid_st);
    if (c->ev_grid_ready) cudaEventDestroy(c->ev_grid_ready);
    for (auto& e : c->ev_class_ready) if (e) cudaEventDestroy(e);
    if (c->copy_st) cudaStreamDestroy(c->copy_st);
@@ -908,8 +945,10 @@ static int upload_begin(sbq_ctx* c) {
    };
    for (auto& r : c->class_ready) r = false;
    c->grid_ready = false;
-   if (!c->grid_list.empty() && c->grid_list.size() <= 16) {
-      const int rc = copy_loci(c->grid_list);
+   if (!(c->grid_list.empty() && c->sgrid_list.empty()) && c->grid_list.size() + c->sgrid_list.size() <= 16) {
+      int rc = copy_loci(c->grid_list);
+      if (rc) return rc;
+      rc = copy_loci(c->sgrid_list);
       if (rc) return rc;
       CU(cudaEventRecord(c->ev_grid_ready, st));
       c->grid_ready = true;
@@ -1160,46 +1199,87 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
    c->stats.grid_em_ms = 0;
    for (auto& t : c->lt) t.used = false;
    const bool pending = c->upload_pending;   // asynchronous upload in flight: every launch waits for the copies it needs only
+   // one class of grid-tier loci (full grid on the main stream / sub-grid on its own stream): two-slot kernel for the loci that
+   // qualify, TMA ring or register-staged kernel for the rest; the one-off layout passes run on the first solve of an upload
+   auto launch_grid_part = [&](const std::vector<int32_t>& list, size_t list_off, size_t n_dual_, const std::vector<int64_t>& rec_off, int max_iso_rest,
+                               bool tma_ok, const cudaDeviceProp& prop_, DevBuf& scratch, DevBuf& rowrec, DevBuf& pkbuf, cudaStream_t gs_, int& variant,
+                               int& n_launch) -> int {
+      int rc = 0;
+      variant = 0;
+      const int32_t* d_grid = c->d_lists_p + list_off;
+      const int n_dual = (int)n_dual_, n_rest = (int)list.size() - n_dual;
+      if (n_dual) {
+         GridDualBufs bf{&scratch.p, &scratch.cap, &c->d_col16.p, &c->d_col16.cap, &rowrec.p, &rowrec.cap, &pkbuf.p, &pkbuf.cap};
+         int nl = 0;
+         std::vector<int> h_iso((size_t)n_dual);
+         for (int i = 0; i < n_dual; ++i) h_iso[i] = c->meta[list[i]].T;
+         rc = grid_dual_launch(c->dp, c->nnz, d_grid, n_dual, h_iso.data(), rec_off.data(), prop_, bf, c->col16_ready, gs_, &nl);
+         n_launch += nl;
+         variant = 3;
+      }
+      if (rc == 0 && n_rest) {   // loci the two-slot layout does not take (wide, or rows too long on average)
+         int nl = 0;
+         if (tma_ok && !getenv("SBQ_GRID_NO_TMA")) {
+            if (!variant) variant = 2;
+            rc = grid_tma_launch(c->dp, c->nnz, d_grid + n_dual, n_rest, max_iso_rest, prop_, &scratch.p, &scratch.cap,
+                                 &c->d_col16.p, &c->d_col16.cap, c->col16_ready, gs_, &nl);
+         } else {
+            if (!variant) variant = 1;
+            rc = grid_tier_launch(c->dp, d_grid + n_dual, n_rest, prop_, &scratch.p, &scratch.cap, gs_, &nl);
+         }
+         n_launch += nl;
+      }
+      return rc;
+   };
+   auto grid_failed = [&](int rc) -> int {
+      // the one-off layout passes permute alpha inside each giant row IN PLACE: after a failure the resident copy can no
+      // longer be trusted to match the column arrays, so the batch has to be uploaded again
+      c->resident = false;
+      c->col16_ready = false;
+      return fail(c, rc < -6 ? SBQ_ERR_CUDA : rc, "grid tier launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+   };
+   if (!(c->grid_list.empty() && c->sgrid_list.empty())) {
+      // the 16-bit slot array is shared by both classes (indexed by non-zero): sized here, so that neither launch re-allocates it
+      // under the other
+      const size_t need16 = (size_t)c->nnz * 2 + 256;
+      if (need16 > c->d_col16.cap) {
+         if (!c->d_col16.reserve(need16)) return fail(c, SBQ_ERR_NOMEM, "device allocation failed (16-bit slots)");
+         c->col16_ready = false;
+      }
+   }
    if (!c->grid_list.empty()) {
       if (pending) CU(cudaStreamWaitEvent(st, c->grid_ready ? c->ev_grid_ready : c->ev[1], 0));
       CU(cudaEventRecord(c->ev[6], st));
       int n_launch = 0;
-      int rc = 0;
-      c->grid_variant = 0;
-      const int32_t* d_grid = c->d_lists_p + c->grid_list_off;
-      const int n_dual = (int)c->grid_n_dual, n_rest = (int)c->grid_list.size() - n_dual;
-      if (n_dual) {
-         GridDualBufs bf{&c->d_grid_scratch.p, &c->d_grid_scratch.cap, &c->d_col16.p, &c->d_col16.cap, &c->d_rowrec.p, &c->d_rowrec.cap, &c->d_pk.p, &c->d_pk.cap};
-         int nl = 0;
-         std::vector<int> h_iso((size_t)n_dual);
-         for (int i = 0; i < n_dual; ++i) h_iso[i] = c->meta[c->grid_list[i]].T;
-         rc = grid_dual_launch(c->dp, c->nnz, d_grid, n_dual, h_iso.data(), c->grid_rec_off.data(), c->prop, bf, c->col16_ready, st, &nl);
-         n_launch += nl;
-         c->grid_variant = 3;
-      }
-      if (rc == 0 && n_rest) {   // loci the two-slot layout does not take (wide, or rows too long on average)
-         int nl = 0;
-         if (c->grid_tma_ok && !getenv("SBQ_GRID_NO_TMA")) {
-            if (!c->grid_variant) c->grid_variant = 2;
-            rc = grid_tma_launch(c->dp, c->nnz, d_grid + n_dual, n_rest, c->grid_max_iso, c->prop, &c->d_grid_scratch.p, &c->d_grid_scratch.cap,
-                                 &c->d_col16.p, &c->d_col16.cap, c->col16_ready, st, &nl);
-         } else {
-            if (!c->grid_variant) c->grid_variant = 1;
-            rc = grid_tier_launch(c->dp, d_grid + n_dual, n_rest, c->prop, &c->d_grid_scratch.p, &c->d_grid_scratch.cap, st, &nl);
-         }
-         n_launch += nl;
-      }
-      if (rc == 0) c->col16_ready = true;
-      if (rc != 0) {
-         // the one-off layout passes permute alpha inside each giant row IN PLACE: after a failure the resident copy can no
-         // longer be trusted to match the column arrays, so the batch has to be uploaded again
-         c->resident = false;
-         c->col16_ready = false;
-         return fail(c, rc < -6 ? SBQ_ERR_CUDA : rc, "grid tier launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-      }
+      const int rc = launch_grid_part(c->grid_list, c->grid_list_off, c->grid_n_dual, c->grid_rec_off, c->grid_max_iso, c->grid_tma_ok, c->prop,
+                                      c->d_grid_scratch, c->d_rowrec, c->d_pk, st, c->grid_variant, n_launch);
+      if (rc != 0) return grid_failed(rc);
       launches += n_launch;
       CU(cudaEventRecord(c->ev[7], st));
    }
+   c->lt_sgrid.used = false;
+   if (!c->sgrid_list.empty()) {
+      // small giants: same kernels on SGRID_CTAS CTAs (the launchers size their grids by prop.multiProcessorCount), own stream,
+      // launched before the cluster classes so that the sub-grid is resident when they fill the other SMs
+      cudaDeviceProp prop_sg = c->prop;
+      prop_sg.multiProcessorCount = std::min(SGRID_CTAS, c->prop.multiProcessorCount);
+      cudaStream_t gs_ = c->sgrid_st;
+      CU(cudaStreamWaitEvent(gs_, c->ev_fork, 0));
+      if (pending) CU(cudaStreamWaitEvent(gs_, c->grid_ready ? c->ev_grid_ready : c->ev[1], 0));
+      if (!c->grid_list.empty()) {                      // the full-grid class owns the GPU first
+         CU(cudaStreamWaitEvent(gs_, c->ev[7], 0));
+      }
+      CU(cudaEventRecord(c->lt_sgrid.e0, gs_));
+      int n_launch = 0;
+      const int rc = launch_grid_part(c->sgrid_list, c->sgrid_list_off, c->sgrid_n_dual, c->sgrid_rec_off, c->sgrid_max_iso, c->sgrid_tma_ok, prop_sg,
+                                      c->d_sgrid_scratch, c->d_srowrec, c->d_spk, gs_, c->sgrid_variant, n_launch);
+      if (rc != 0) return grid_failed(rc);
+      launches += n_launch;
+      CU(cudaEventRecord(c->lt_sgrid.e1, gs_));
+      CU(cudaEventRecord(c->ev_sgrid_join, gs_));
+      c->lt_sgrid.used = true;
+   }
+   if (!(c->grid_list.empty() && c->sgrid_list.empty())) c->col16_ready = true;
    const bool serialize = getenv("SBQ_SERIALIZE") != nullptr;   // debugging / profiling: one stream, isolated kernel times
    // Launch ORDER (class i keeps stream / timer / ready-event i whatever its position). The work distributor serves
    // kernels roughly in launch order, 16- and 8-CTA clusters strand a few SMs per GPC that only single CTAs can use, and the
@@ -1265,6 +1345,7 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
       CU(cudaEventRecord(c->ev_join[i], c->side[i]));
       CU(cudaStreamWaitEvent(st, c->ev_join[i], 0));
    }
+   if (c->lt_sgrid.used) CU(cudaStreamWaitEvent(st, c->ev_sgrid_join, 0));
    CU(cudaEventRecord(c->ev[3], st));
    fpkm_sum_kernel<<<1, 1024, 0, st>>>(dp.locus_fpkm, c->n_loci, c->d_fpkm_sum);
    CU(cudaGetLastError());
@@ -1297,6 +1378,11 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
    };
    if (c->lt[0].used) { CU(cudaEventElapsedTime(&ms, c->lt[0].e0, c->lt[0].e1)); add_stat(1, 1, 1, c->warp_list, ms, c->lt[0].e0); }
    if (!c->grid_list.empty()) { add_stat(3, 0, 32, c->grid_list, c->stats.grid_em_ms, c->ev[6]); c->launch_stats.back().variant = c->grid_variant; }
+   if (c->lt_sgrid.used) {      // sub-grid class: cluster_size field = its CTA count
+      CU(cudaEventElapsedTime(&ms, c->lt_sgrid.e0, c->lt_sgrid.e1));
+      add_stat(3, std::min(SGRID_CTAS, c->prop.multiProcessorCount), 32, c->sgrid_list, ms, c->lt_sgrid.e0);
+      c->launch_stats.back().variant = c->sgrid_variant;
+   }
    for (size_t i = 0; i < c->classes.size(); ++i) {
       LaunchTimer& t = c->lt[2 + i % N_SIDE_STREAMS];
       CU(cudaEventElapsedTime(&ms, t.e0, t.e1));

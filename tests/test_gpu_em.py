@@ -332,6 +332,29 @@ def test_grid_tier_two_slot_wide_loci(q, oracle_mod, monkeypatch, T):
     assert_matches_oracle(res, ora, b, "two-slot grid kernel, T = %d" % T)
 
 
+def test_small_giants_run_on_a_sub_grid_beside_the_other_tiers(q, oracle_mod, monkeypatch):
+    """Grid-tier loci below 4 M non-zeros ("small giants") are solved by the same grid kernels on a 32-CTA sub-grid, on a stream
+    of their own, while the cluster and warp tiers use the other SMs. Planner-chosen tiers (nothing forced): a sparse small giant
+    (two-slot kernel) and a dense one (TMA ring kernel) inside a human-shaped batch, every locus against the oracle, bit-
+    reproducible when solved again, and identical to the full-grid solve of the same loci to the tolerance of the oracle test."""
+    rng = np.random.default_rng(11)
+    dense = _shape_locus(rng, 200, 2600, 125)
+    dense["total_mapped_reads"] = int(dense["count"].sum())
+    b = synth.concat([synth.human_shaped(n_loci=300, total_fragments=150_000, seed=9, max_rows=400), synth.giant(n_loci=1, rows_per_locus=8000, seed=5), dense])
+    ora = oracle_mod.quantify_batch(b, b["total_mapped_reads"], n_threads=2)
+    monkeypatch.setenv("SBQ_DUAL_VERIFY", "1")
+    res = run_gpu(q, b)
+    sub = [r for r in q.launch_stats() if r["kernel"].startswith("em_grid")]
+    assert len(sub) == 1 and sub[0]["cluster_size"] == 32 and sub[0]["n_loci"] == 2, sub        # both on the sub-grid
+    assert res["stats"]["loci_grid"] == 2 and res["stats"]["loci_warp"] > 0 and res["stats"]["loci_cta"] > 0
+    assert_matches_oracle(res, ora, b, "small giants on a sub-grid")
+    q.solve(b["total_mapped_reads"])
+    q.finalize_tpm(q.fpkm_sum())
+    q.download()
+    again = q.results()
+    assert np.array_equal(res["theta"], again["theta"]) and np.array_equal(res["iters"], again["iters"])
+
+
 def test_grid_tier_two_slot_rows_with_unsorted_columns(q, oracle_mod, monkeypatch):
     """The two-slot layout pairs rows by merging their (ascending) column lists; a row whose columns are not strictly
     ascending (out of contract: sbq_validate rejects it, but validation is optional) must stay in CSR order and be walked

@@ -201,3 +201,20 @@ def test_stopping_rule_within_floating_point_noise_of_the_threshold(sbq_lib_path
         it_g, th_g = solve(norms[k], tier)
         assert abs(it_g - it_o) <= 1, (tier, it_g, it_o)
         assert np.linalg.norm(th_g - th_o) <= norms[k] * (1 + 1e-9)
+
+
+@pytest.mark.gpu
+def test_calls_on_a_closed_quantifier_fail_loudly(sbq_lib_path):
+    """close() destroys the context; the Python handle is cleared, so a later call gets SBQ_ERR_INVALID from the NULL check of
+    every entry point instead of touching freed memory (seen as a std::system_error abort in a profiling script)."""
+    from strawberry_b200 import api
+    b = synth.human_shaped(n_loci=10, total_fragments=2000, seed=3, max_rows=40)
+    q = api.Quantifier()
+    q.submit_flat(b)
+    q.run(b["total_mapped_reads"])
+    q.close()
+    q.close()                                   # idempotent
+    for call in (lambda: q.submit_flat(b), lambda: q.run(1000), lambda: q.solve(1000), q.clear):
+        with pytest.raises(api.SbqError) as e:
+            call()
+        assert e.value.code == api.SBQ_ERR_INVALID

@@ -1,3 +1,7 @@
 #!/bin/bash
-SBQ_LIB_PATH=build/variants/libsbq_nofence.so timeout 300 python tools/prof.py giant 1000000 40 2>&1 | grep -E "grid GB"
-SBQ_LIB_PATH=build/variants/libsbq_phases.so timeout 300 python tools/prof.py giant 1000000 40 2>&1 | grep -E "G6PHASES|grid GB" | tail -2
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_robustness.py -x -q -m gpu 2>&1 | tail -3
+for tool in racecheck synccheck memcheck; do
+  timeout 1200 compute-sanitizer --tool $tool python tools/sanitize.py > gpurun_out/r02g_sanitize_$tool.log 2>&1
+  grep -E "ok|SUMMARY|ERROR|terminate" gpurun_out/r02g_sanitize_$tool.log | tail -13
+done

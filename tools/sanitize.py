@@ -1,6 +1,6 @@
 """Small all-tier workload for compute-sanitizer (memcheck / racecheck / synccheck): warp tier, cluster tier with cluster
 sizes 1 / 4 / 16 (64-, 128- and 512-thread CTAs; all-to-all and owner exchange), grid tier (two-slot kernel incl. its layout and
-packing passes, TMA ring kernel), the bias kernels (warp tier and clusters of 1 - 16 CTAs), the on-device generator, the device
+packing passes, TMA ring kernel; full grid and the 32-CTA sub-grid of the "small giants" running beside the other tiers), the bias kernels (warp tier and clusters of 1 - 16 CTAs), the on-device generator, the device
 class-table builder and the GPU class weights."""
 import os
 import sys
@@ -30,6 +30,12 @@ for tier, cs, it in ((0, 0, 30), (2, 1, 10), (2, 4, 10), (2, 16, 10), (3, 0, 6))
     r = q.results()
     print("tier", tier, "cs", cs, "ok", np.isfinite(r["theta"]).all(), q.stats()["kernel_launches"])
     q.close()
+q = api.Quantifier(max_iter=3)                            # planner-chosen tiers with a "small giant": 32-CTA sub-grid on its own stream beside the other tiers
+bs = synth.concat([b, synth.giant(n_loci=1, rows_per_locus=7000, seed=6)])
+q.submit_flat(bs)
+q.run(bs["total_mapped_reads"])
+print("sub-grid ok", np.isfinite(q.results()["theta"]).all(), [r["cluster_size"] for r in q.launch_stats() if r["kernel"].startswith("em_grid")])
+q.close()
 q = api.Quantifier(bias_mode=1, max_out_it=2, max_theta_it=4, max_bias_it=2)     # bias kernels: warp tier + clusters of 1 .. 16 CTAs
 bb = synth.concat([b] + [synth.giant(n_loci=1, rows_per_locus=r, seed=4) for r in (200, 600, 1500)])     # + 9.6 k / 29 k / 72 k non-zeros: clusters of 2, 4, 8
 q.submit_flat(bb)
