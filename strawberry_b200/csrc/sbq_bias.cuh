@@ -375,6 +375,7 @@ em_bias_kernel(DevParams p, BiasParams bp, const int32_t* __restrict__ list, int
 // leg of the benchmark was bound by ONE 15-row locus that needs 77 573 theta iterations).
 // --------------------------------------------------------------------------------------------
 constexpr int BW_WARPS = 4;
+constexpr int BW_REG = 8;    // non-zeros per row a lane keeps in registers on the single-row fast path
 __host__ __device__ inline size_t bias_warp_smem_bytes() { return (size_t)BW_WARPS * ((size_t)WT_MAX_ISO * WT_STRIDE + WT_MAX_ISO) * sizeof(double); }
 __host__ __device__ inline bool bias_warp_tier(int64_t nnz, int R, int T) { return T <= WT_MAX_ISO && R <= WT_MAX_ROWS && nnz <= WT_MAX_NNZ; }
 
@@ -429,6 +430,18 @@ em_bias_warp_kernel(DevParams p, BiasParams bp, const int32_t* __restrict__ list
       tot = warp_sum_ll(tot);
       kept = (int)warp_sum_ll(kept);
       __syncwarp();
+      // fast path: one row per lane, at most BW_REG non-zeros each, held in registers for the whole solve (same order of every sum
+      // as the general path: padding entries carry alpha = 0). The locus that bounds the benchmark's bias leg - 15 rows, 41
+      // non-zeros, 77 573 theta iterations - runs here.
+      const bool fast = R <= 32 && __all_sync(0xffffffffu, (int)(k1[0] - k0[0]) <= BW_REG);
+      double ra[BW_REG];
+      int rc[BW_REG];
+#pragma unroll
+      for (int e = 0; e < BW_REG; ++e) {
+         const bool v = fast && ne[0] >= 0 && k0[0] + e < k1[0];
+         ra[e] = v ? al[k0[0] + e] : 0.0;
+         rc[e] = v ? col[k0[0] + e] : 0;
+      }
       // column sum over the lanes, fixed order (lane j: column j); clears the accumulators
       auto col_sum = [&]() -> double {
          double s0 = 0.0;
@@ -448,10 +461,16 @@ em_bias_warp_kernel(DevParams p, BiasParams bp, const int32_t* __restrict__ list
          for (int out = 0; out < bp.max_out_it && status == LOCUS_ITER_CAP; ++out) {
             outer = out + 1;
             // s_j = sum_i alpha_ij w_i over the kept rows
+            if (fast) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q)
-               if (ne[q] >= 0)
-                  for (int64_t k = k0[q]; k < k1[q]; ++k) acc[col[k] * WT_STRIDE + lane] += al[k] * w[q];
+               for (int e = 0; e < BW_REG; ++e)
+                  if (ra[e] != 0.0) acc[rc[e] * WT_STRIDE + lane] += ra[e] * w[0];
+            } else {
+#pragma unroll
+               for (int q = 0; q < 2; ++q)
+                  if (ne[q] >= 0)
+                     for (int64_t k = k0[q]; k < k1[q]; ++k) acc[col[k] * WT_STRIDE + lane] += al[k] * w[q];
+            }
             __syncwarp();
             const double s = col_sum();
             __syncwarp();
@@ -461,14 +480,30 @@ em_bias_warp_kernel(DevParams p, BiasParams bp, const int32_t* __restrict__ list
                ++iters;
                if (lane < T) th[lane] = (s != 0) ? cur / s : 0.0;
                __syncwarp();
+               if (fast) {
+                  double t[BW_REG], dd = 0.0;
 #pragma unroll
-               for (int q = 0; q < 2; ++q) {
-                  if (ne[q] < 0) continue;
-                  double dd = 0.0;
-                  for (int64_t k = k0[q]; k < k1[q]; ++k) dd += al[k] * th[col[k]];
-                  if (dd == 0) { zero = true; continue; }
-                  const double r = (double)ne[q] / dd;
-                  for (int64_t k = k0[q]; k < k1[q]; ++k) { const int c = col[k]; acc[c * WT_STRIDE + lane] += al[k] * th[c] * r; }
+                  for (int e = 0; e < BW_REG; ++e) { t[e] = th[rc[e]]; dd += ra[e] * t[e]; }
+                  if (ne[0] >= 0) {
+                     if (dd == 0) {
+                        zero = true;
+                     } else {
+                        const double r = (double)ne[0] / dd;
+#pragma unroll
+                        for (int e = 0; e < BW_REG; ++e)
+                           if (ra[e] != 0.0) acc[rc[e] * WT_STRIDE + lane] += ra[e] * t[e] * r;
+                     }
+                  }
+               } else {
+#pragma unroll
+                  for (int q = 0; q < 2; ++q) {
+                     if (ne[q] < 0) continue;
+                     double dd = 0.0;
+                     for (int64_t k = k0[q]; k < k1[q]; ++k) dd += al[k] * th[col[k]];
+                     if (dd == 0) { zero = true; continue; }
+                     const double r = (double)ne[q] / dd;
+                     for (int64_t k = k0[q]; k < k1[q]; ++k) { const int c = col[k]; acc[c * WT_STRIDE + lane] += al[k] * th[c] * r; }
+                  }
                }
                zero = __any_sync(0xffffffffu, zero);
                __syncwarp();
@@ -485,11 +520,18 @@ em_bias_warp_kernel(DevParams p, BiasParams bp, const int32_t* __restrict__ list
             // (2) bias-weight update: Newton steps on beta with d_i fixed
             if (lane < T) th[lane] = (s != 0) ? cur / s : 0.0;
             __syncwarp();
+            if (fast) {
+               d[0] = 0.0;
+               d[1] = 0.0;
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-               d[q] = 0.0;
-               if (ne[q] >= 0)
-                  for (int64_t k = k0[q]; k < k1[q]; ++k) d[q] += al[k] * th[col[k]];
+               for (int e = 0; e < BW_REG; ++e) d[0] += ra[e] * th[rc[e]];
+            } else {
+#pragma unroll
+               for (int q = 0; q < 2; ++q) {
+                  d[q] = 0.0;
+                  if (ne[q] >= 0)
+                     for (int64_t k = k0[q]; k < k1[q]; ++k) d[q] += al[k] * th[col[k]];
+               }
             }
             __syncwarp();
             double bprev[BI_MAX_COV];
