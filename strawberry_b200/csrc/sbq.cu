@@ -37,6 +37,9 @@ namespace {
 
 constexpr size_t SMEM_CAP = CL_SMEM_CAP;   // dynamic shared memory we ask for at most (227 KB usable)
 constexpr int N_SIDE_STREAMS = 12;
+#ifndef SBQ_DEFAULT_WARP_CTAS
+#define SBQ_DEFAULT_WARP_CTAS 0   // 0 = SMs x occupancy
+#endif
 #ifndef SBQ_DEFAULT_ORDER
 #define SBQ_DEFAULT_ORDER 0
 #endif
@@ -1307,7 +1310,9 @@ int sbq_solve(sbq_ctx* c, int64_t total_mapped_reads) {
       const int n = (int)c->warp_list.size();
       int per_sm = 1;
       CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_warp_kernel, WT_WARPS * 32, smem));
-      const int grid = std::max(1, std::min((n + WT_WARPS - 1) / WT_WARPS, per_sm * c->prop.multiProcessorCount));
+      int grid = std::max(1, std::min((n + WT_WARPS - 1) / WT_WARPS, per_sm * c->prop.multiProcessorCount));
+      static const int warp_cta_cap = getenv("SBQ_WARP_CTAS") ? atoi(getenv("SBQ_WARP_CTAS")) : SBQ_DEFAULT_WARP_CTAS;   // persistent warps: the grid only sets the parallelism
+      if (warp_cta_cap > 0) grid = std::min(grid, warp_cta_cap);
       int* queue = (int*)((char*)c->d_fpkm_sum + 64);
       if (pending) CU(cudaStreamWaitEvent(st, c->ev[1], 0));   // many small loci all over the batch: they need everything
       CU(cudaMemsetAsync(queue, 0, sizeof(int), st));
