@@ -228,7 +228,8 @@ int  sbq_locus_devices(sbq_ctx*, int32_t* device_of_locus);
  * theta receives n_iso doubles; returns the sbq_locus_status (>= 0) or a negative sbq_error. */
 int  sbq_em_solve(sbq_ctx*, const sbq_locus* locus, double* theta, int32_t* iters);
 
-/* Bias mode (bias_mode = 1, OUR definition - DESIGN.md section 7; no reference behaviour exists). Per-row
+/* Bias mode (bias_mode = 1, OUR definition - DESIGN.md section 7; no reference behaviour exists). Loci of up to 2165 isoforms
+ * (sbq_solve returns SBQ_ERR_UNSUPPORTED beyond: 13 T doubles of shared memory per CTA). Per-row
  * covariates x[n_row][n_cov] (row-major, rows in submit order, n_cov <= 6) must be set after the last sbq_submit*
  * and before sbq_upload / sbq_run; sbq_bias_results returns beta[n_loci][n_cov] and the outer rounds per locus. */
 int  sbq_set_covariates(sbq_ctx*, const double* x, int64_t n_row, int32_t n_cov);

@@ -123,10 +123,12 @@ int  sbq_fetch_alpha(sbq_ctx*, double* alpha);
  * the batch on the GPU: compatibility (Contig::is_compatible), class coordinates (overlap_exons), first-seen class ids,
  * code-blind set semantics of ExonBin::_frags, float class masses, the class x isoform CSR and the weight descriptors that
  * weights_kernel turns into alpha. Integer results are bit-identical to sbq_build_locus (tests/test_gpu_rawbuild.py). A batch
- * is either all raw loci or none; raw batches are single-device. What the kernels cannot reproduce bit-exactly - fragment
+ * is either all raw loci or none. In a multi-GPU context (n_gpus > 1) every raw locus is dealt to a device when it is submitted -
+ * the device with the least hits x isoforms so far; its non-zeros are not known before the table exists - and the devices build
+ * their tables concurrently; results come back in submit order. What the kernels cannot reproduce bit-exactly - fragment
  * masses that are not multiples of 1/2 (--allow-multimapped-hits), a hit touching more than 16 exon segments, a class spanning
  * more than 32 segments of an isoform - makes sbq_upload return SBQ_ERR_UNSUPPORTED: use sbq_build_locus for such a batch.
- * sbq_fetch_raw_classes (tests) copies the device-built table out; the CSR comes from sbq_fetch_batch. */
+ * sbq_fetch_raw_classes (tests, single-device contexts) copies the device-built table out; the CSR comes from sbq_fetch_batch. */
 int  sbq_submit_raw(sbq_ctx*, const sbq_locus_input* in, int64_t* locus_index /* may be NULL: position of the locus in the batch (submit order) */);
 int  sbq_fetch_raw_classes(sbq_ctx*, int32_t* hit_class, uint8_t* hit_ncoord, uint16_t* hit_coords, int64_t* class_rep, float* class_mass,
                            int32_t* class_nfrag);

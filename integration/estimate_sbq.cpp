@@ -138,7 +138,7 @@ void LocusContext::assign_exon_bin(const vector<Contig>& hits, const vector<Geno
    // Class assignment on the device as well (sbq_submit_raw): the locus is queued as it is - flattened hits and isoforms - and
    // the whole class table of the sample is built by CUDA kernels during sbq_upload. Fragment masses must be multiples of 1/2
    // (true unless --allow-multimapped-hits), -f needs the table on the host; SBQ_HOST_CLASSES=1 keeps the host builder.
-   tl_raw = defer && use_only_unique_hits && !getenv("SBQ_HOST_CLASSES") && !(getenv("SBQ_N_GPUS") && atoi(getenv("SBQ_N_GPUS")) > 1);   // raw batches are single-device
+   tl_raw = defer && use_only_unique_hits && !getenv("SBQ_HOST_CLASSES");   // (on N GPUs libsbq deals every raw locus to a device at submit time)
    if (defer && !g_model_set.load()) {      // the context's insert model and read length (once per sample)
       lock_guard<mutex> lk(g_ctx_mu);
       if (!g_model_set.load()) {

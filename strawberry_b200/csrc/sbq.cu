@@ -787,6 +787,8 @@ int sbq_clear(sbq_ctx* c) {
       cudaStreamSynchronize(c->copy_st);
       c->upload_pending = false;
    }
+   if (c->multi && c->raw_mode)
+      for (sbq_ctx* ch : c->multi->child) sbq_clear(ch);   // raw loci are staged in the children
    reset_batch(c);
    return SBQ_SUCCESS;
 }
@@ -1608,8 +1610,8 @@ int sbq_submit_deferred(sbq_ctx* c, const sbq_table* const* tables, int64_t n_ta
 // ---- raw loci: fragment-class assignment on the device (sbq_rawbuild.cuh) ---------------------------------------------
 int sbq_submit_raw(sbq_ctx* c, const sbq_locus_input* in, int64_t* locus_index) {
    if (!c || !in || in->n_iso < 1 || in->n_hit < 0 || !in->iso_feat_ptr || (in->n_hit > 0 && (!in->hit_feat_ptr || !in->hit_mass))) return SBQ_ERR_INVALID;
-   if (c->multi) return fail(c, SBQ_ERR_UNSUPPORTED, "raw loci are single-device");
    if (c->cfg.bias_mode) return fail(c, SBQ_ERR_UNSUPPORTED, "raw loci carry no covariates");
+   if (c->multi) return multi_submit_raw(c, in, locus_index);
    if (in->n_iso > SBQ_MAX_ISO) return fail(c, SBQ_ERR_UNSUPPORTED, "%d isoforms > SBQ_MAX_ISO", in->n_iso);
    // static part of the class table on the host (cheap, O(exons + T S)): disjoint exon segments, isoform segment lists, lengths
    sbq_locus_input st = *in;
@@ -1886,6 +1888,7 @@ extern "C" {
 int sbq_fetch_raw_classes(sbq_ctx* c, int32_t* hit_class, uint8_t* hit_ncoord, uint16_t* hit_coords, int64_t* class_rep, float* class_mass, int32_t* class_nfrag) {
    if (!c) return SBQ_ERR_INVALID;
    std::lock_guard<std::mutex> lk(c->mu);
+   if (c->multi) return fail(c, SBQ_ERR_UNSUPPORTED, "sbq_fetch_raw_classes is single-device (a test aid)");
    CU(cudaSetDevice(c->device));
    if (!c->resident || !c->raw_mode) return fail(c, SBQ_ERR_STATE, "sbq_fetch_raw_classes needs an uploaded raw batch");
    const RawBatch& b = c->rb;

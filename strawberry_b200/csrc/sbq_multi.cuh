@@ -61,6 +61,7 @@ struct MultiState {
    std::vector<double*> d_sum;                   // per device: [0] local FPKM sum (input), [1] all-reduced sum (output)
    std::vector<int32_t> owner;                   // locus -> child (valid after sbq_upload)
    std::vector<std::vector<int32_t>> loci_of;    // child -> its loci, ascending submit order
+   std::vector<int64_t> raw_load;                // raw batches: work dealt to every child so far (hits x isoforms)
    bool reduced = false;                         // the all-reduce of the current solve has been enqueued
    double global_sum = 0.0;
 };
@@ -187,10 +188,57 @@ int multi_gather(sbq_ctx* par, sbq_ctx* ch, const std::vector<int32_t>& list) {
    return SBQ_SUCCESS;
 }
 
+// Raw loci (class assignment on the device, sbq_submit_raw) on N devices. The non-zeros of a raw locus are not known before its
+// device has built the class table, so the locus is dealt at SUBMIT time: to the device with the least work so far, work = hits x
+// isoforms (what the compatibility pass and, through the classes, the EM scale with). A function of the submit sequence only.
+// The locus is staged directly in that device's context; sbq_upload then builds every device's class tables concurrently.
+int multi_submit_raw(sbq_ctx* c, const sbq_locus_input* in, int64_t* locus_index) {
+   MultiState& m = *c->multi;
+   std::lock_guard<std::mutex> lk(c->mu);
+   if (c->host_released || (c->n_loci > 0 && !c->raw_mode)) return fail(c, SBQ_ERR_STATE, "a batch is either all raw loci or none");
+   const size_t n = m.child.size();
+   if (c->n_loci == 0) {
+      for (sbq_ctx* ch : m.child) sbq_clear(ch);
+      m.owner.clear();
+      for (auto& v : m.loci_of) v.clear();
+      m.raw_load.assign(n, 0);
+   }
+   size_t k = 0;
+   for (size_t i = 1; i < n; ++i)
+      if (m.raw_load[i] < m.raw_load[k]) k = i;
+   const int rc = sbq_submit_raw(m.child[k], in, nullptr);
+   if (rc) return fail(c, rc, "device %d: %s", m.devices[k], m.child[k]->err.c_str());
+   m.raw_load[k] += (int64_t)in->n_hit * in->n_iso + in->n_hit + in->n_iso;
+   m.owner.push_back((int32_t)k);
+   m.loci_of[k].push_back((int32_t)c->n_loci);
+   if (locus_index) *locus_index = c->n_loci;
+   c->n_loci += 1;
+   c->n_iso += in->n_iso;
+   c->raw_mode = true;
+   c->deferred = 1;
+   c->resident = c->solved = c->downloaded = false;
+   return SBQ_SUCCESS;
+}
+
 int multi_upload(sbq_ctx* c) {
    MultiState& m = *c->multi;
    std::lock_guard<std::mutex> lk(c->mu);
    if (c->n_loci == 0) return fail(c, SBQ_ERR_STATE, "nothing submitted");
+   if (c->raw_mode) {   // the loci already sit in their devices' contexts
+      for (sbq_ctx* ch : m.child) {
+         sbq_set_plan(ch, c->force_tier, c->force_cluster);
+         ch->model = c->model;
+         ch->model_emp = c->model_emp;
+         ch->model_read_len = c->model_read_len;
+         ch->have_model = c->have_model;
+      }
+      const int rcr = multi_for_each(c, [&](int i) { return sbq_upload(m.child[i]); });
+      if (rcr) return rcr;
+      m.reduced = false;
+      c->resident = true;
+      c->solved = c->downloaded = false;
+      return SBQ_SUCCESS;
+   }
    if (c->host_released) return fail(c, SBQ_ERR_STATE, "the borrowed batch was released by the previous sbq_upload: sbq_clear and submit again");
    if (c->deferred == 1 && !c->have_model) return fail(c, SBQ_ERR_STATE, "deferred weights need sbq_set_insert_model()");
    if (c->cfg.bias_mode == 1 && !c->have_cov) return fail(c, SBQ_ERR_STATE, "bias_mode = 1 needs sbq_set_covariates() after the last submit");

@@ -122,3 +122,34 @@ def test_integrated_binary_on_n_gpus_gives_the_same_gtf(tmp_path):
                        stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600, env=dict(os.environ, **env))
         outs.append(sorted(l for l in open(out, "rb").read().split(b"\n") if l and not l.startswith(b"#")))
     assert len(outs[0]) > 500 and outs[0] == outs[1]
+
+
+def test_raw_loci_on_two_gpus_match_one():
+    """Device class assignment (sbq_submit_raw) in a 2-GPU context: every raw locus is dealt to a device at submit time, the class
+    tables are built on both devices concurrently, results come back in submit order - bitwise equal to the single-device
+    context (theta / FPKM / frac / keep / iters / status; TPM up to the order of one sum)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import locusgen
+    from strawberry_b200 import api, builder
+    loci = []
+    for seed in range(40, 64):
+        isoforms, hits, _ = locusgen.random_locus(seed)
+        loci.append(([locusgen.transcript_features(ex) for ex in isoforms], [(m, builder.pair_features(l, r)) for m, l, r in hits]))
+    out = []
+    for n in (1, 2):
+        q = api.Quantifier(device=0, n_gpus=n, min_iso_frac=0.01)
+        q.set_insert_model(builder.Model.normal(200.0, 40.0), 50)
+        for tfe, hl in loci:
+            builder.submit_raw(q, tfe, hl, read_len=50)
+        q.run(250_000)
+        out.append((q.results(), q.locus_devices(), q.stats()))
+        q.close()
+    (ref, _, st1), (got, dev, st2) = out
+    for k in ("theta", "fpkm", "frac", "keep", "iters", "status"):
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
+    assert np.allclose(got["tpm"], ref["tpm"], rtol=1e-12, equal_nan=True)
+    assert sorted(set(dev.tolist())) == [0, 1]
+    assert st2["n_loci"] == st1["n_loci"] == len(loci) and st2["nnz"] == st1["nnz"] and st2["n_row"] == st1["n_row"]

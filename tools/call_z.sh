@@ -1,2 +1,3 @@
 #!/bin/bash
-for o in 0 2 3; do for c in 0 16 24 32 48; do SBQ_ORDER=$o SBQ_WARP_CTAS=$c timeout 120 python tools/ab_quick.py order $o warp_ctas $c 2>&1 | tail -1; done; done
+nvidia-smi -L | wc -l
+timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_rawbuild.py -x -q 2>&1 | tail -5
