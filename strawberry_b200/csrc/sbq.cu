@@ -332,7 +332,7 @@ constexpr int N_BUCKETS = 5;
 const int BUCKET_NT[N_BUCKETS] = {64, 128, 512, 512, 512};
 int smem_bucket(size_t bytes) { return bytes <= 12 * 1024 ? 0 : bytes <= 24 * 1024 ? 1 : bytes <= 56 * 1024 ? 2 : bytes <= 112 * 1024 ? 3 : 4; }
 
-constexpr int64_t SGRID_MAX_NNZ = 4 * 1000 * 1000;   // grid-tier loci below this run on a sub-grid ...
+constexpr int64_t SGRID_MAX_NNZ = 1000 * 1000;       // grid-tier loci below this run on a sub-grid (their passes are barrier latency; above, bandwidth starts to count) ...
 constexpr int SGRID_CTAS = 32;                       // ... of this many CTAs (one per SM), beside the other tiers
 
 int cluster_size_for(int64_t nnz) {

@@ -333,7 +333,7 @@ def test_grid_tier_two_slot_wide_loci(q, oracle_mod, monkeypatch, T):
 
 
 def test_small_giants_run_on_a_sub_grid_beside_the_other_tiers(q, oracle_mod, monkeypatch):
-    """Grid-tier loci below 4 M non-zeros ("small giants") are solved by the same grid kernels on a 32-CTA sub-grid, on a stream
+    """Grid-tier loci below 1 M non-zeros ("small giants") are solved by the same grid kernels on a 32-CTA sub-grid, on a stream
     of their own, while the cluster and warp tiers use the other SMs. Planner-chosen tiers (nothing forced): a sparse small giant
     (two-slot kernel) and a dense one (TMA ring kernel) inside a human-shaped batch, every locus against the oracle, bit-
     reproducible when solved again, and identical to the full-grid solve of the same loci to the tolerance of the oracle test."""
