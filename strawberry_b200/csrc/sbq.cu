@@ -333,7 +333,12 @@ const int BUCKET_NT[N_BUCKETS] = {64, 128, 512, 512, 512};
 int smem_bucket(size_t bytes) { return bytes <= 12 * 1024 ? 0 : bytes <= 24 * 1024 ? 1 : bytes <= 56 * 1024 ? 2 : bytes <= 112 * 1024 ? 3 : 4; }
 
 constexpr int64_t SGRID_MAX_NNZ = 1000 * 1000;       // grid-tier loci below this run on a sub-grid (their passes are barrier latency; above, bandwidth starts to count) ...
-constexpr int SGRID_CTAS = 32;                       // ... of this many CTAs (one per SM), beside the other tiers
+constexpr int SGRID_CTAS_DEFAULT = 32;               // ... of this many CTAs (one per SM), beside the other tiers
+inline int sgrid_ctas() {                            // SBQ_SGRID_CTAS overrides (tuning aid; changes the summation order of those loci)
+   static const int v = getenv("SBQ_SGRID_CTAS") ? std::max(1, atoi(getenv("SBQ_SGRID_CTAS"))) : SGRID_CTAS_DEFAULT;
+   return v;
+}
+#define SGRID_CTAS sgrid_ctas()
 
 int cluster_size_for(int64_t nnz) {
    // ~14 B of shared memory per non-zero (row part + CSC index): a CTA's slice stays under ~14k non-zeros, which still
