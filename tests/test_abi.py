@@ -60,3 +60,39 @@ def test_product_does_not_touch_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), f
                 assert "liboracle" not in text and "libsbref" not in text and "sbq_oracle" not in text, f
+
+
+def test_shipped_cubin_is_sm100a_and_uses_the_blackwell_features(sbq_lib_path):
+    """Static check of the shipped library (no GPU needed): the only device code is an sm_100a cubin, no kernel spills to
+    local memory, the giant-locus kernels stage their rows with 1-D TMA bulk copies (SASS UBLKCP) behind mbarriers (SYNCS),
+    and the cluster-tier kernels (EM and bias) use the hardware cluster barrier (UCGABAR_*). tools/sass_summary.py prints
+    the full table (profiles/r02_sass_summary.txt)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    elf = subprocess.run([cuobjdump, "-lelf", sbq_lib_path], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", elf))
+    assert archs == {"sm_100a"}, archs
+    res = subprocess.run([cuobjdump, "-res-usage", sbq_lib_path], capture_output=True, text=True).stdout
+    local = [int(x) for x in re.findall(r"LOCAL:(\d+)", res)]
+    assert local and max(local) == 0, "a kernel spills to local memory"
+    sass = subprocess.run([cuobjdump, "-sass", sbq_lib_path], capture_output=True, text=True).stdout
+    per_kernel, cur = {}, None
+    for line in sass.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            per_kernel[cur] = set()
+            continue
+        m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+        if cur and m:
+            per_kernel[cur].add(m.group(1))
+    def ops(substr):
+        return [v for k, v in per_kernel.items() if substr in k]
+    assert ops("em_grid_dual_kernel") and all({"UBLKCP", "SYNCS"} <= o for o in ops("em_grid_dual_kernel"))
+    assert ops("em_grid_tma_kernel") and all({"UBLKCP", "SYNCS"} <= o for o in ops("em_grid_tma_kernel"))
+    assert ops("em_cluster_kernel") and all({"UCGABAR_ARV", "UCGABAR_WAIT"} <= o for o in ops("em_cluster_kernel"))
+    assert ops("em_bias_kernel") and all({"UCGABAR_ARV", "UCGABAR_WAIT"} <= o for o in ops("em_bias_kernel"))
+    assert not any("HMMA" in o or "IMMA" in o for o in per_kernel.values())    # sparse gather + reduction: no tensor-core path by design
